@@ -1,0 +1,337 @@
+// model_prep.hpp — one-off host preparation of the device model blob.
+//
+// What the reference recomputes on every run_tracks()/run() call (PhyloCSFModel_make,
+// src/instance.hpp:687-712: Q from the ECM, eigendecomposition, all P(t_b); lpr_leaves rebuilding
+// every P again, src/fixed_lik.hpp:370-372; get_prior, :281-360) is done here ONCE per model:
+//   * Q (instance.hpp:648-685), its real eigensystem (instance.hpp:309-434; symmetrised Jacobi instead
+//     of gsl_eigen_nonsymmv — Q is reversible, so D^{1/2} Q D^{-1/2} is symmetric), pi (equilibrium row
+//     of S^-1 at argmin|lambda|), P_b = S diag(exp(lambda t_b)) S^-1 with the reference's clamp /
+//     diagonal fix-up / error checks (instance.hpp:487-640), t_b = double(float(double(bl_b) * rho))
+//     (instance.hpp:299-307; newick_elem::branch_length is a float);
+//   * the pruning program: a children-first traversal that finishes the subtree needing more live
+//     partials first (values are order independent, fixed_lik.hpp:135-157), flattened into
+//     GATHER/PUSH/POP/GEMM ops, plus the P matrices of the GEMM edges re-ordered into DMMA fragment order;
+//   * the BLS program: post-order node list with 128-bit "species below" masks and the pointer tree's
+//     double branch lengths (additional_scores.hpp:5-41).
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace pcsf {
+
+constexpr int NS = 64;
+
+// ---- pruning program ops (int32: code << 16 | arg) -------------------------------------------------
+enum : int32_t { OP_GATHER_SET = 1, OP_GATHER_MUL = 2, OP_PUSH = 3, OP_POP_MUL = 4, OP_GEMM = 5, OP_END = 6 };
+inline int32_t mk_op(int code, int arg) { return (code << 16) | (arg & 0xffff); }
+
+struct BlsNode {            // one post-order entry of the BLS program
+    double bl;              // newick_node::branch_length (double)
+    uint64_t self_lo, self_hi;   // leaves below this node
+    uint64_t left_lo, left_hi;   // leaves below the left child (0 for leaves)
+    int32_t is_leaf;
+    int32_t pad;
+};
+
+struct EcmHost {
+    double lambda[NS], SR[NS * NS], SRinv[NS * NS], pi[NS], logpi[NS];
+    std::vector<double> P;        // (n-1) x 64 x 64 at rho = 1, row-major P[a][b]
+    std::vector<double> pstream;  // n_gemm tiles of 4096 doubles, DMMA fragment order, program order
+    std::vector<double> leafPT;   // nl x 65 x 64: leafPT[l][x][a] = P_l[a][x], x = 64 -> row sums
+};
+
+struct ModelHost {
+    int nl = 0, n = 0;
+    std::vector<int16_t> child1, child2;
+    std::vector<float> bl;
+    std::vector<double> bl64;
+    EcmHost ecm[2];
+    std::vector<int32_t> program;
+    std::vector<int> gemm_edges;  // node id of the g-th GEMM op
+    int max_stack = 0;
+    std::vector<BlsNode> bls_prog;
+    int bls_depth = 0;
+    double bls_all = 0.0;         // all_species_branch_length (additional_scores.hpp:56)
+};
+
+// instance.hpp:648-685
+inline void build_q(const double *S, const double *f, double *Q) {
+    double scale = 0.0;
+    for (int i = 0; i < NS; ++i) {
+        double rowsum = 0.0;
+        for (int j = 0; j < NS; ++j) {
+            const double v = S[i * NS + j] * f[j];
+            Q[i * NS + j] = v;
+            rowsum -= v;
+        }
+        Q[i * NS + i] = rowsum;
+        scale -= rowsum * f[i];
+    }
+    for (int i = 0; i < NS * NS; ++i) Q[i] /= scale;
+}
+
+// Symmetric eigenproblem by cyclic Jacobi rotations.  A is overwritten; V's columns are eigenvectors.
+inline void jacobi64(std::vector<double> &A, std::vector<double> &V, double *w) {
+    for (int i = 0; i < NS; ++i)
+        for (int j = 0; j < NS; ++j) V[i * NS + j] = (i == j);
+    for (int sweep = 0; sweep < 128; ++sweep) {
+        double off = 0.0;
+        for (int p = 0; p < NS; ++p)
+            for (int q = p + 1; q < NS; ++q) off += A[p * NS + q] * A[p * NS + q];
+        if (off < 1e-300) break;
+        for (int p = 0; p + 1 < NS; ++p)
+            for (int q = p + 1; q < NS; ++q) {
+                const double apq = A[p * NS + q];
+                if (std::fabs(apq) < 1e-310) continue;
+                const double theta = (A[q * NS + q] - A[p * NS + p]) / (2.0 * apq);
+                const double t = std::copysign(1.0, theta) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < NS; ++k) {
+                    const double x = A[k * NS + p], y = A[k * NS + q];
+                    A[k * NS + p] = c * x - s * y;
+                    A[k * NS + q] = s * x + c * y;
+                }
+                for (int k = 0; k < NS; ++k) {
+                    const double x = A[p * NS + k], y = A[q * NS + k];
+                    A[p * NS + k] = c * x - s * y;
+                    A[q * NS + k] = s * x + c * y;
+                }
+                for (int k = 0; k < NS; ++k) {
+                    const double x = V[k * NS + p], y = V[k * NS + q];
+                    V[k * NS + p] = c * x - s * y;
+                    V[k * NS + q] = s * x + c * y;
+                }
+            }
+    }
+    for (int i = 0; i < NS; ++i) w[i] = A[i * NS + i];
+}
+
+// instance.hpp:309-434 (real spectrum) + fixed_lik.hpp:323-346 (equilibrium)
+inline bool eigen_and_prior(const double *Q, const double *f, EcmHost &e, std::string &err) {
+    double sq[NS];
+    for (int i = 0; i < NS; ++i) {
+        if (!(f[i] > 0.0)) { err = "codon frequencies must be strictly positive"; return false; }
+        sq[i] = std::sqrt(f[i]);
+    }
+    std::vector<double> A(NS * NS), U(NS * NS);
+    for (int i = 0; i < NS; ++i)
+        for (int j = 0; j < NS; ++j) A[i * NS + j] = sq[i] * Q[i * NS + j] / sq[j];
+    for (int i = 0; i < NS; ++i)
+        for (int j = i + 1; j < NS; ++j) A[i * NS + j] = A[j * NS + i] = 0.5 * (A[i * NS + j] + A[j * NS + i]);
+    jacobi64(A, U, e.lambda);
+    for (int i = 0; i < NS; ++i)
+        for (int k = 0; k < NS; ++k) {
+            e.SR[i * NS + k] = U[i * NS + k] / sq[i];
+            e.SRinv[k * NS + i] = U[i * NS + k] * sq[i];
+        }
+    int kmin = 0;
+    double best = std::fabs(e.lambda[0]);
+    for (int k = 1; k < NS; ++k)
+        if (std::fabs(e.lambda[k]) < best) { best = std::fabs(e.lambda[k]); kmin = k; }
+    double mass = 0.0;
+    for (int j = 0; j < NS; ++j) mass += e.SRinv[kmin * NS + j];
+    for (int j = 0; j < NS; ++j) {
+        e.pi[j] = e.SRinv[kmin * NS + j] / mass;
+        e.logpi[j] = std::log(e.pi[j]);
+    }
+    return true;
+}
+
+inline double branch_time(float bl, double rho) { return (double)(float)((double)bl * rho); }
+
+// instance.hpp:487-640, one branch.  0 ok, 1 negative entry beyond tolerance, 2 row sum off.
+inline int pmatrix(const EcmHost &e, double t, double *P) {
+    double ex[NS];
+    std::vector<double> B(NS * NS);
+    for (int k = 0; k < NS; ++k) ex[k] = std::exp(e.lambda[k] * t);
+    for (int k = 0; k < NS; ++k)
+        for (int j = 0; j < NS; ++j) B[k * NS + j] = e.SRinv[k * NS + j] * ex[k];
+    for (int i = 0; i < NS; ++i) {
+        double *row = P + i * NS;
+        for (int j = 0; j < NS; ++j) row[j] = 0.0;
+        for (int k = 0; k < NS; ++k) {
+            const double a = e.SR[i * NS + k];
+            for (int j = 0; j < NS; ++j) row[j] += a * B[k * NS + j];
+        }
+    }
+    for (int i = 0; i < NS; ++i) {
+        double total = 0.0, diag = 1.0;
+        for (int j = 0; j < NS; ++j) {
+            const double cell = P[i * NS + j];
+            total += cell;
+            if (cell < 0.0) {
+                if (std::fabs(cell) > 1e-6) return 1;
+                P[i * NS + j] = 0.0;
+            }
+            if (i != j) diag -= P[i * NS + j];
+        }
+        if (std::fabs(total - 1.0) > 1e-6) return 2;
+        P[i * NS + i] = diag;
+    }
+    return 0;
+}
+
+// DMMA m8n8k4 fragment order of one 64x64 P for the chained, K-permuted GEMM of k_prune:
+//   tile[ks][ntp][lane][e] = P[a][b],  a = 8*(2*ntp+e) + lane/4,  b = 8*(ks/2) + 2*(lane%4) + (ks%2)
+inline void to_fragment_order(const double *P, double *tile) {
+    for (int ks = 0; ks < 16; ++ks)
+        for (int ntp = 0; ntp < 4; ++ntp)
+            for (int lane = 0; lane < 32; ++lane)
+                for (int e = 0; e < 2; ++e) {
+                    const int a = 8 * (2 * ntp + e) + lane / 4;
+                    const int b = 8 * (ks / 2) + 2 * (lane % 4) + (ks % 2);
+                    tile[((ks * 4 + ntp) * 32 + lane) * 2 + e] = P[a * NS + b];
+                }
+}
+
+inline void to_leaf_table(const double *P, double *pt /* 65 x 64 */) {
+    for (int a = 0; a < NS; ++a) {
+        double rs = 0.0;
+        for (int x = 0; x < NS; ++x) {
+            pt[x * NS + a] = P[a * NS + x];
+            rs += P[a * NS + x];   // fixed_lik.hpp:116-118: sum over j ascending
+        }
+        pt[64 * NS + a] = rs;
+    }
+}
+
+namespace detail {
+inline int strahler(const ModelHost &m, int i, std::vector<int> &need) {
+    if (m.child1[i] < 0) return need[i] = 0;
+    const int a = strahler(m, m.child1[i], need), b = strahler(m, m.child2[i], need);
+    int r = (a == b) ? (a == 0 ? 1 : a + 1) : (a > b ? a : b);
+    return need[i] = r;
+}
+// emits ops leaving alpha_i (the partial of node i) in R
+inline void emit_partial(ModelHost &m, int i, const std::vector<int> &need, int &sp);
+// emits ops leaving the message of child c to its parent in R (inner child) — or a gather (leaf child)
+inline void emit_msg(ModelHost &m, int c, const std::vector<int> &need, int &sp, bool first) {
+    if (m.child1[c] < 0) {
+        m.program.push_back(mk_op(first ? OP_GATHER_SET : OP_GATHER_MUL, c));
+    } else {
+        emit_partial(m, c, need, sp);
+        m.program.push_back(mk_op(OP_GEMM, (int)m.gemm_edges.size()));
+        m.gemm_edges.push_back(c);
+    }
+}
+inline void emit_partial(ModelHost &m, int i, const std::vector<int> &need, int &sp) {
+    const int c1 = m.child1[i], c2 = m.child2[i];
+    const bool l1 = m.child1[c1] < 0, l2 = m.child1[c2] < 0;
+    if (l1 && l2) {
+        emit_msg(m, c1, need, sp, true);
+        emit_msg(m, c2, need, sp, false);
+    } else if (l1 != l2) {
+        const int inner = l1 ? c2 : c1, leaf = l1 ? c1 : c2;
+        emit_msg(m, inner, need, sp, true);
+        emit_msg(m, leaf, need, sp, false);
+    } else {
+        const int first = need[c1] >= need[c2] ? c1 : c2, second = first == c1 ? c2 : c1;
+        emit_msg(m, first, need, sp, true);
+        m.program.push_back(mk_op(OP_PUSH, 0));
+        ++sp;
+        if (sp > m.max_stack) m.max_stack = sp;
+        emit_msg(m, second, need, sp, true);
+        m.program.push_back(mk_op(OP_POP_MUL, 0));
+        --sp;
+    }
+}
+inline void bls_walk(ModelHost &m, int i, uint64_t &lo, uint64_t &hi, int &depth_out) {
+    BlsNode e{};
+    e.bl = m.bl64[i];
+    if (m.child1[i] < 0) {
+        e.is_leaf = 1;
+        if (i < 64) e.self_lo = 1ull << i; else e.self_hi = 1ull << (i - 64);
+        lo = e.self_lo; hi = e.self_hi;
+        depth_out = 1;
+        m.bls_prog.push_back(e);
+        return;
+    }
+    uint64_t llo, lhi, rlo, rhi;
+    int dl, dr;
+    bls_walk(m, m.child1[i], llo, lhi, dl);
+    bls_walk(m, m.child2[i], rlo, rhi, dr);
+    e.left_lo = llo; e.left_hi = lhi;
+    e.self_lo = llo | rlo; e.self_hi = lhi | rhi;
+    lo = e.self_lo; hi = e.self_hi;
+    depth_out = dl > dr + 1 ? dl : dr + 1;
+    m.bls_prog.push_back(e);
+}
+}  // namespace detail
+
+// Host restatement of newick_sum_branch_lengths over the BLS program (also what k_bls executes).
+inline double bls_eval_host(const ModelHost &m, uint64_t mlo, uint64_t mhi) {
+    std::vector<double> st(m.bls_depth + 2);
+    int sp = 0;
+    for (const BlsNode &e : m.bls_prog) {
+        if (e.is_leaf) { st[sp++] = e.bl; continue; }
+        const double r = st[--sp], l = st[--sp];
+        const uint64_t rlo = e.self_lo & ~e.left_lo, rhi = e.self_hi & ~e.left_hi;
+        const bool ol = ((mlo & e.left_lo) | (mhi & e.left_hi)) != 0;
+        const bool orr = ((mlo & rlo) | (mhi & rhi)) != 0;
+        const bool arrived = ((mlo & ~e.self_lo) | (mhi & ~e.self_hi)) != 0;
+        double v = arrived ? e.bl : 0.0;
+        if (ol) v += l;
+        if (orr) v += r;
+        st[sp++] = v;
+    }
+    return st[0];
+}
+
+// Returns "" on success.
+inline std::string prepare_model(ModelHost &m, int nl, const int16_t *c1, const int16_t *c2, const float *bl,
+                                 const double *bl64, const double *const S[2], const double *const f[2]) {
+    m.nl = nl;
+    m.n = 2 * nl - 1;
+    m.child1.assign(c1, c1 + m.n);
+    m.child2.assign(c2, c2 + m.n);
+    m.bl.assign(bl, bl + m.n);
+    m.bl64.assign(bl64, bl64 + m.n);
+    for (int i = 0; i < m.n; ++i) {
+        const bool leaf = i < nl;
+        if (leaf != (c1[i] < 0) || leaf != (c2[i] < 0)) return "tree is not in newick_flatten order (leaves first)";
+        if (!leaf && (c1[i] >= i || c2[i] >= i || c1[i] < 0 || c2[i] < 0)) return "inner nodes must follow their children";
+    }
+    // pruning program
+    std::vector<int> need(m.n);
+    detail::strahler(m, m.n - 1, need);
+    int sp = 0;
+    m.program.clear(); m.gemm_edges.clear(); m.max_stack = 0;
+    detail::emit_partial(m, m.n - 1, need, sp);
+    m.program.push_back(mk_op(OP_END, 0));
+    if ((int)m.gemm_edges.size() != nl - 2) return "internal error: GEMM count";
+    // BLS program
+    uint64_t lo, hi;
+    m.bls_prog.clear();
+    detail::bls_walk(m, m.n - 1, lo, hi, m.bls_depth);
+    {
+        const uint64_t alo = nl >= 64 ? ~0ull : ((1ull << nl) - 1);
+        const uint64_t ahi = nl > 64 ? (nl >= 128 ? ~0ull : ((1ull << (nl - 64)) - 1)) : 0ull;
+        m.bls_all = bls_eval_host(m, alo, ahi);
+    }
+    // the two ECMs
+    for (int w = 0; w < 2; ++w) {
+        EcmHost &e = m.ecm[w];
+        std::vector<double> Q(NS * NS);
+        std::string err;
+        build_q(S[w], f[w], Q.data());
+        if (!eigen_and_prior(Q.data(), f[w], e, err)) return err;
+        e.P.resize((size_t)(m.n - 1) * NS * NS);
+        for (int b = 0; b < m.n - 1; ++b) {
+            const int rc = pmatrix(e, branch_time(m.bl[b], 1.0), e.P.data() + (size_t)b * NS * NS);
+            if (rc) return std::string("CamlPaml.Q.substition_matrix check failed for branch ") + std::to_string(b) +
+                           (rc == 1 ? " (entry < 0)" : " (row sum != 1)");
+        }
+        e.pstream.resize(m.gemm_edges.size() * (size_t)NS * NS);
+        for (size_t g = 0; g < m.gemm_edges.size(); ++g)
+            to_fragment_order(e.P.data() + (size_t)m.gemm_edges[g] * NS * NS, e.pstream.data() + g * NS * NS);
+        e.leafPT.resize((size_t)nl * 65 * NS);
+        for (int l = 0; l < nl; ++l) to_leaf_table(e.P.data() + (size_t)l * NS * NS, e.leafPT.data() + (size_t)l * 65 * NS);
+    }
+    return "";
+}
+
+}  // namespace pcsf

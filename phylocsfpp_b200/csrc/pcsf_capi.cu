@@ -1,0 +1,495 @@
+// pcsf_capi.cu — C-ABI (include/phylocsf_b200.h) over the sm_100a kernels in kernels.cuh.
+//
+// Replaces the reference's call seam run_tracks / run / compute_bls_score (src/run.hpp:35,57,
+// src/additional_scores.hpp:44).  No CPU fallback: every compute entry point needs a CUDA device.
+#include "../../include/phylocsf_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "mle.cuh"
+
+using namespace pcsf;
+
+static thread_local std::string g_err;
+static pcsf_status fail(pcsf_status st, const std::string &msg) { g_err = msg; return st; }
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(PCSF_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct pcsf_model {
+    int device = 0;
+    int sm_count = 148;
+    ModelHost host;
+    // device blob
+    double *d_pstream[2] = {nullptr, nullptr}, *d_leafPT[2] = {nullptr, nullptr};
+    double *d_pi[2] = {nullptr, nullptr}, *d_logpi[2] = {nullptr, nullptr};
+    double *d_eig[2] = {nullptr, nullptr};   // lambda[64] | SR[4096] | SRinv[4096]
+    int32_t *d_program = nullptr;
+    BlsNode *d_bls_prog = nullptr;
+    float *d_bl = nullptr;
+    int32_t *d_gemm_edges = nullptr;
+    // scratch
+    DevBuf codes, klo, khi, slot, flag, uniq, pidx, table, slotmin, bsums, logz, anc, misc, io_in, io_out, perwin, mle;
+    int *d_bad = nullptr;
+    uint32_t *d_nuniq = nullptr;       // [max chunks]
+    int64_t chunk_cols = (int64_t)1 << 22;
+    bool timing = false;
+    pcsf_tracks_stats last{};
+    int64_t last_nwin = 0;
+    int last_chunks = 0;
+    int64_t codes_ld = 0;
+    size_t prune_smem = 0;
+    cudaEvent_t ev[8] = {};
+};
+
+static const int MAX_CHUNKS = 4096;
+
+extern "C" const char *pcsf_last_error(void) { return g_err.c_str(); }
+extern "C" int pcsf_abi_version(void) { return PCSF_ABI_VERSION; }
+
+static pcsf_status upload(const void *src, size_t bytes, void **dst) {
+    CK(cudaMalloc(dst, bytes ? bytes : 16));
+    if (bytes) CK(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+    return PCSF_OK;
+}
+
+extern "C" pcsf_status pcsf_model_create(const pcsf_model_desc *d, int device, pcsf_model **out) {
+    if (!d || !out || d->nl < 2 || !d->child1 || !d->child2 || !d->branch_len || !d->branch_len_f64 || !d->ecm_c ||
+        !d->freq_c || !d->ecm_nc || !d->freq_nc)
+        return fail(PCSF_ERR_INVALID, "pcsf_model_create: null argument or fewer than 2 leaves");
+    if (d->nl > PCSF_MAX_LEAVES) return fail(PCSF_ERR_UNSUPPORTED, "more than 128 leaves are not supported");
+    pcsf_model *m = new pcsf_model;
+    const double *S[2] = {d->ecm_c, d->ecm_nc}, *f[2] = {d->freq_c, d->freq_nc};
+    const std::string err = prepare_model(m->host, d->nl, d->child1, d->child2, d->branch_len, d->branch_len_f64, S, f);
+    if (!err.empty()) {
+        delete m;
+        return fail(err.find("substition_matrix") != std::string::npos ? PCSF_ERR_NUMERIC : PCSF_ERR_INVALID, err);
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+        delete m;
+        return fail(PCSF_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    m->device = device;
+    CK(cudaSetDevice(device));
+    CK(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device));
+    {
+        uint8_t lut[256];
+        memset(lut, 255, sizeof lut);
+        lut['A'] = lut['a'] = 0; lut['C'] = lut['c'] = 1; lut['G'] = lut['g'] = 2; lut['T'] = lut['t'] = 3;
+        lut['.'] = lut['-'] = lut['N'] = lut['n'] = 4;
+        CK(cudaMemcpyToSymbol(c_dna_lut, lut, sizeof lut));
+    }
+    pcsf_status st;
+    for (int w = 0; w < 2; ++w) {
+        const EcmHost &e = m->host.ecm[w];
+        if ((st = upload(e.pstream.data(), e.pstream.size() * 8, (void **)&m->d_pstream[w]))) return st;
+        if ((st = upload(e.leafPT.data(), e.leafPT.size() * 8, (void **)&m->d_leafPT[w]))) return st;
+        if ((st = upload(e.pi, 64 * 8, (void **)&m->d_pi[w]))) return st;
+        if ((st = upload(e.logpi, 64 * 8, (void **)&m->d_logpi[w]))) return st;
+        std::vector<double> eig(64 + 2 * 4096);
+        memcpy(eig.data(), e.lambda, 64 * 8);
+        memcpy(eig.data() + 64, e.SR, 4096 * 8);
+        memcpy(eig.data() + 64 + 4096, e.SRinv, 4096 * 8);
+        if ((st = upload(eig.data(), eig.size() * 8, (void **)&m->d_eig[w]))) return st;
+    }
+    if ((st = upload(m->host.program.data(), m->host.program.size() * 4, (void **)&m->d_program))) return st;
+    if ((st = upload(m->host.bls_prog.data(), m->host.bls_prog.size() * sizeof(BlsNode), (void **)&m->d_bls_prog))) return st;
+    if ((st = upload(m->host.bl.data(), m->host.bl.size() * 4, (void **)&m->d_bl))) return st;
+    {
+        std::vector<int32_t> ge(m->host.gemm_edges.begin(), m->host.gemm_edges.end());
+        if ((st = upload(ge.data(), ge.size() * 4, (void **)&m->d_gemm_edges))) return st;
+    }
+    CK(cudaMalloc(&m->d_bad, sizeof(int)));
+    CK(cudaMemset(m->d_bad, 0, sizeof(int)));
+    CK(cudaMalloc(&m->d_nuniq, sizeof(uint32_t) * MAX_CHUNKS));
+    for (auto &e : m->ev) CK(cudaEventCreate(&e));
+    m->prune_smem = prune_smem_bytes(m->host.nl, (int)m->host.program.size(), m->host.max_stack);
+    if (m->prune_smem > 227 * 1024) {
+        return fail(PCSF_ERR_UNSUPPORTED, "tree needs more shared memory than one SM has (stack depth " +
+                                              std::to_string(m->host.max_stack) + ")");
+    }
+    CK(cudaFuncSetAttribute(k_prune, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->prune_smem));
+    CK(cudaFuncSetAttribute(k_bls, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            std::max(1, m->host.bls_depth) * BLS_THREADS * 8));
+    if ((st = mle_setup(m->host))) return fail(st, "mle kernel setup failed");
+    *out = m;
+    return PCSF_OK;
+}
+
+extern "C" void pcsf_model_destroy(pcsf_model *m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    for (int w = 0; w < 2; ++w) {
+        cudaFree(m->d_pstream[w]); cudaFree(m->d_leafPT[w]); cudaFree(m->d_pi[w]); cudaFree(m->d_logpi[w]);
+        cudaFree(m->d_eig[w]);
+    }
+    cudaFree(m->d_program); cudaFree(m->d_bls_prog); cudaFree(m->d_bl); cudaFree(m->d_gemm_edges);
+    cudaFree(m->d_bad); cudaFree(m->d_nuniq);
+    DevBuf *bufs[] = {&m->codes, &m->klo, &m->khi, &m->slot, &m->flag, &m->uniq, &m->pidx, &m->table, &m->slotmin,
+                      &m->bsums, &m->logz, &m->anc, &m->misc, &m->io_in, &m->io_out, &m->perwin, &m->mle};
+    for (DevBuf *b : bufs) b->release();
+    for (auto &e : m->ev) if (e) cudaEventDestroy(e);
+    delete m;
+}
+
+extern "C" pcsf_status pcsf_model_get(const pcsf_model *m, int which, double *lambda, double *pi, double *P) {
+    if (!m || which < 0 || which > 1) return fail(PCSF_ERR_INVALID, "pcsf_model_get: bad argument");
+    const EcmHost &e = m->host.ecm[which];
+    if (lambda) memcpy(lambda, e.lambda, 64 * 8);
+    if (pi) memcpy(pi, e.pi, 64 * 8);
+    if (P) memcpy(P, e.P.data(), e.P.size() * 8);
+    return PCSF_OK;
+}
+
+extern "C" pcsf_status pcsf_set_chunk_columns(pcsf_model *m, int64_t columns) {
+    if (!m || columns < 0) return fail(PCSF_ERR_INVALID, "pcsf_set_chunk_columns: bad argument");
+    if (columns == 0) columns = (int64_t)1 << 22;
+    if (columns > ((int64_t)1 << 23)) columns = (int64_t)1 << 23;   // window ids are 32-bit, scan is 2-level
+    m->chunk_cols = columns;
+    return PCSF_OK;
+}
+
+extern "C" pcsf_status pcsf_set_timing(pcsf_model *m, int enabled) {
+    if (!m) return fail(PCSF_ERR_INVALID, "null model");
+    m->timing = enabled != 0;
+    return PCSF_OK;
+}
+
+static inline uint32_t next_pow2(uint64_t x) {
+    uint64_t p = 1;
+    while (p < x) p <<= 1;
+    return (uint32_t)p;
+}
+
+// dedup + prune for one window space of `nwin` local windows; results land in m->pidx (pattern id per
+// window), m->logz / m->anc (per pattern); *d_nuniq_slot receives the pattern count.
+static pcsf_status dedup_and_prune(pcsf_model *m, const WinSpace &ws, uint32_t nwin, bool dedup, bool want_anc,
+                                   uint32_t *d_nuniq_slot, uint32_t *d_pattern_out, int64_t out_base,
+                                   cudaStream_t st, float *ms_hash, float *ms_dedup, float *ms_prune) {
+    const int TB = 256;
+    const uint32_t nblk = (nwin + TB - 1) / TB;
+    CK(m->uniq.reserve((size_t)nwin * 4));
+    CK(m->pidx.reserve((size_t)nwin * 4));
+    CK(m->logz.reserve((size_t)nwin * 16));
+    if (want_anc) CK(m->anc.reserve((size_t)nwin * 16));
+    if (m->timing) CK(cudaEventRecord(m->ev[0], st));
+    if (dedup) {
+        CK(m->klo.reserve((size_t)nwin * 8));
+        CK(m->khi.reserve((size_t)nwin * 8));
+        if (ws.mode == 0) {
+            const int64_t ncols = nwin / 2;
+            k_keys_tracks<<<(unsigned)((ncols + TB - 1) / TB), TB, 0, st>>>(ws, ncols, m->klo.as<ulonglong2>(),
+                                                                           m->khi.as<ulonglong2>());
+        } else {
+            k_keys_list<<<nblk, TB, 0, st>>>(ws, nwin, m->klo.as<uint64_t>(), m->khi.as<uint64_t>());
+        }
+        CK(cudaGetLastError());
+        if (m->timing) CK(cudaEventRecord(m->ev[1], st));
+        const uint32_t T = next_pow2((uint64_t)nwin * 2 < 1024 ? 1024 : (uint64_t)nwin * 2);
+        const uint32_t nsb = (nwin + SCAN_BLOCK - 1) / SCAN_BLOCK;
+        CK(m->table.reserve((size_t)T * 4));
+        CK(m->slotmin.reserve((size_t)T * 4));
+        CK(m->slot.reserve((size_t)nwin * 4));
+        CK(m->flag.reserve((size_t)nwin * 4));
+        CK(m->bsums.reserve((size_t)(nsb + 1) * 4));
+        CK(cudaMemsetAsync(m->table.p, 0xFF, (size_t)T * 4, st));
+        CK(cudaMemsetAsync(m->slotmin.p, 0xFF, (size_t)T * 4, st));
+        k_insert<<<nblk, TB, 0, st>>>(m->klo.as<uint64_t>(), m->khi.as<uint64_t>(), nwin, m->table.as<uint32_t>(), T - 1,
+                                      m->slot.as<uint32_t>(), m->slotmin.as<uint32_t>());
+        k_resolve<<<nblk, TB, 0, st>>>(nwin, m->slot.as<uint32_t>(), m->slotmin.as<uint32_t>(), m->flag.as<uint32_t>());
+        k_scan_blocks<<<nsb, SCAN_THREADS, 0, st>>>(m->flag.as<uint32_t>(), nwin, m->bsums.as<uint32_t>());
+        k_scan_sums<<<1, 1024, 0, st>>>(m->bsums.as<uint32_t>(), nsb, d_nuniq_slot);
+        k_finalize<<<nblk, TB, 0, st>>>(nwin, m->slot.as<uint32_t>(), m->flag.as<uint32_t>(), m->bsums.as<uint32_t>(),
+                                        m->uniq.as<uint32_t>(), m->pidx.as<uint32_t>(), d_pattern_out, out_base);
+        CK(cudaGetLastError());
+    } else {
+        if (m->timing) CK(cudaEventRecord(m->ev[1], st));
+        k_identity<<<nblk, TB, 0, st>>>(nwin, m->uniq.as<uint32_t>(), m->pidx.as<uint32_t>(), d_nuniq_slot, d_pattern_out,
+                                        out_base);
+        CK(cudaGetLastError());
+    }
+    if (m->timing) CK(cudaEventRecord(m->ev[2], st));
+    PruneArgs pa{};
+    pa.ws = ws;
+    pa.uniq = m->uniq.as<uint32_t>();
+    pa.n_unique = d_nuniq_slot;
+    pa.program = m->d_program;
+    pa.n_ops = (int)m->host.program.size();
+    pa.n_gemm = (int)m->host.gemm_edges.size();
+    pa.max_stack = m->host.max_stack;
+    for (int w = 0; w < 2; ++w) {
+        pa.pstream[w] = m->d_pstream[w];
+        pa.leafPT[w] = m->d_leafPT[w];
+        pa.pi[w] = m->d_pi[w];
+        pa.logpi[w] = m->d_logpi[w];
+        pa.logz[w] = m->logz.as<double>() + (size_t)w * nwin;
+        pa.anc[w] = want_anc ? m->anc.as<double>() + (size_t)w * nwin : nullptr;
+    }
+    const uint32_t max_tiles = (nwin + PR_TILE_W - 1) / PR_TILE_W;
+    const unsigned grid = std::min<uint32_t>((uint32_t)m->sm_count, std::max<uint32_t>(1u, max_tiles));
+    k_prune<<<grid, PR_THREADS, m->prune_smem, st>>>(pa);
+    CK(cudaGetLastError());
+    if (m->timing) {
+        CK(cudaEventRecord(m->ev[3], st));
+        CK(cudaEventSynchronize(m->ev[3]));
+        float t;
+        CK(cudaEventElapsedTime(&t, m->ev[0], m->ev[1])); *ms_hash += t;
+        CK(cudaEventElapsedTime(&t, m->ev[1], m->ev[2])); *ms_dedup += t;
+        CK(cudaEventElapsedTime(&t, m->ev[2], m->ev[3])); *ms_prune += t;
+    }
+    return PCSF_OK;
+}
+
+static pcsf_status run_pack(pcsf_model *m, const uint8_t *d_seqs, int64_t L, int64_t ld, cudaStream_t st) {
+    const int nl = m->host.nl;
+    m->codes_ld = ((L + 16 + 15) / 16) * 16;
+    CK(m->codes.reserve((size_t)m->codes_ld * nl));
+    CK(cudaMemsetAsync(m->d_bad, 0, sizeof(int), st));
+    const int64_t nvec = m->codes_ld / 16;
+    dim3 grid((unsigned)std::min<int64_t>((nvec + 255) / 256, 65535), nl);
+    k_pack<<<grid, 256, 0, st>>>(d_seqs, L, ld, nl, m->codes.as<uint8_t>(), m->codes_ld, m->d_bad);
+    CK(cudaGetLastError());
+    return PCSF_OK;
+}
+
+static pcsf_status run_bls(pcsf_model *m, int64_t L, int raw, double *d_out, cudaStream_t st) {
+    if (L <= 0) return PCSF_OK;
+    const size_t sh = (size_t)std::max(1, m->host.bls_depth) * BLS_THREADS * 8;
+    k_bls<<<(unsigned)((L + BLS_THREADS - 1) / BLS_THREADS), BLS_THREADS, sh, st>>>(
+        m->codes.as<uint8_t>(), m->codes_ld, m->host.nl, L, m->d_bls_prog, (int)m->host.bls_prog.size(),
+        m->host.bls_depth, m->host.bls_all, raw, d_out);
+    CK(cudaGetLastError());
+    return PCSF_OK;
+}
+
+extern "C" pcsf_status pcsf_tracks_device(pcsf_model *m, const uint8_t *d_seqs, int64_t L, int64_t ld, uint32_t flags,
+                                          double *d_plus, double *d_minus, double *d_bls, uint32_t *d_pattern_index,
+                                          void *cuda_stream) {
+    if (!m || L < 0 || ld < L || (L > 0 && !d_seqs)) return fail(PCSF_ERR_INVALID, "pcsf_tracks: bad argument");
+    if ((flags & PCSF_TRACKS_SCORES) && L > 2 && (!d_plus || !d_minus)) return fail(PCSF_ERR_INVALID, "plus/minus required");
+    if ((flags & PCSF_TRACKS_BLS) && L > 0 && !d_bls) return fail(PCSF_ERR_INVALID, "bls required");
+    if (flags & PCSF_TRACKS_FP32) return fail(PCSF_ERR_UNSUPPORTED, "the FP32-class tensor path is not built yet");
+    CK(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    m->last = pcsf_tracks_stats{};
+    m->last_nwin = 0;
+    m->last_chunks = 0;
+    if (L == 0) return PCSF_OK;
+    pcsf_status rc;
+    if (m->timing) CK(cudaEventRecord(m->ev[4], st));
+    if ((rc = run_pack(m, d_seqs, L, ld, st))) return rc;
+    if (m->timing) CK(cudaEventRecord(m->ev[5], st));
+    if (flags & PCSF_TRACKS_BLS) {
+        if ((rc = run_bls(m, L, 0, d_bls, st))) return rc;
+    }
+    if (m->timing) {
+        CK(cudaEventRecord(m->ev[6], st));
+        CK(cudaEventSynchronize(m->ev[6]));
+        CK(cudaEventElapsedTime(&m->last.ms_pack, m->ev[4], m->ev[5]));
+        CK(cudaEventElapsedTime(&m->last.ms_bls, m->ev[5], m->ev[6]));
+    }
+    const int64_t W = L - 2;
+    if ((flags & PCSF_TRACKS_SCORES) && W > 0) {
+        const int64_t nchunks = (W + m->chunk_cols - 1) / m->chunk_cols;
+        if (nchunks > MAX_CHUNKS) return fail(PCSF_ERR_INVALID, "too many chunks; raise pcsf_set_chunk_columns");
+        for (int64_t c = 0; c < nchunks; ++c) {
+            const int64_t c0 = c * m->chunk_cols, c1 = std::min(W, c0 + m->chunk_cols);
+            const uint32_t nwin = (uint32_t)(2 * (c1 - c0));
+            WinSpace ws{m->codes.as<uint8_t>(), m->codes_ld, m->host.nl, 0, c0, nullptr};
+            if ((rc = dedup_and_prune(m, ws, nwin, !(flags & PCSF_TRACKS_NO_DEDUP), false, m->d_nuniq + c, d_pattern_index,
+                                      2 * c0, st, &m->last.ms_hash, &m->last.ms_dedup, &m->last.ms_prune)))
+                return rc;
+            if (m->timing) CK(cudaEventRecord(m->ev[0], st));
+            k_scatter_tracks<<<(nwin + 255) / 256, 256, 0, st>>>(nwin, m->pidx.as<uint32_t>(), m->logz.as<double>(),
+                                                                 m->logz.as<double>() + nwin, c0, d_plus, d_minus);
+            CK(cudaGetLastError());
+            if (m->timing) {
+                CK(cudaEventRecord(m->ev[1], st));
+                CK(cudaEventSynchronize(m->ev[1]));
+                float t;
+                CK(cudaEventElapsedTime(&t, m->ev[0], m->ev[1]));
+                m->last.ms_scatter += t;
+            }
+        }
+        m->last_chunks = (int)nchunks;
+        m->last_nwin = 2 * W;
+    }
+    return PCSF_OK;
+}
+
+extern "C" pcsf_status pcsf_tracks_device_finish(pcsf_model *m, void *cuda_stream, pcsf_tracks_stats *stats) {
+    if (!m) return fail(PCSF_ERR_INVALID, "null model");
+    CK(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CK(cudaStreamSynchronize(st));
+    int bad = 0;
+    CK(cudaMemcpy(&bad, m->d_bad, sizeof(int), cudaMemcpyDeviceToHost));
+    m->last.n_windows = m->last_nwin;
+    m->last.n_chunks = m->last_chunks;
+    m->last.n_unique = 0;
+    if (m->last_chunks > 0) {
+        std::vector<uint32_t> nu(m->last_chunks);
+        CK(cudaMemcpy(nu.data(), m->d_nuniq, sizeof(uint32_t) * m->last_chunks, cudaMemcpyDeviceToHost));
+        for (uint32_t v : nu) m->last.n_unique += v;
+    }
+    if (stats) *stats = m->last;
+    if (bad) return fail(PCSF_ERR_BAD_CHAR, "alignment contains a character outside ACGTacgt.-Nn (reference: exit(37))");
+    return PCSF_OK;
+}
+
+extern "C" pcsf_status pcsf_tracks(pcsf_model *m, const uint8_t *seqs, int64_t L, int64_t ld, uint32_t flags, double *plus,
+                                   double *minus, double *bls, uint32_t *pattern_index, pcsf_tracks_stats *stats) {
+    if (!m || L < 0 || ld < L || (L > 0 && !seqs)) return fail(PCSF_ERR_INVALID, "pcsf_tracks: bad argument");
+    CK(cudaSetDevice(m->device));
+    if (stats) *stats = pcsf_tracks_stats{};
+    if (L == 0) return PCSF_OK;
+    const int nl = m->host.nl;
+    const int64_t W = std::max<int64_t>(L - 2, 0);
+    const int64_t ldd = ((L + 15) / 16) * 16;
+    CK(m->io_in.reserve((size_t)ldd * nl));
+    const size_t out_bytes = (size_t)W * 16 + (size_t)L * 8 + (pattern_index ? (size_t)W * 8 : 0) + 64;
+    CK(m->io_out.reserve(out_bytes));
+    CK(cudaMemcpy2D(m->io_in.p, (size_t)ldd, seqs, (size_t)ld, (size_t)L, (size_t)nl, cudaMemcpyHostToDevice));
+    double *d_plus = m->io_out.as<double>(), *d_minus = d_plus + W, *d_bls = d_minus + W;
+    uint32_t *d_pat = pattern_index ? reinterpret_cast<uint32_t *>(d_bls + L) : nullptr;
+    pcsf_status rc = pcsf_tracks_device(m, m->io_in.as<uint8_t>(), L, ldd, flags, d_plus, d_minus, d_bls, d_pat, nullptr);
+    if (rc) return rc;
+    rc = pcsf_tracks_device_finish(m, nullptr, stats);
+    if (rc) return rc;
+    if ((flags & PCSF_TRACKS_SCORES) && W > 0) {
+        CK(cudaMemcpy(plus, d_plus, (size_t)W * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(minus, d_minus, (size_t)W * 8, cudaMemcpyDeviceToHost));
+        if (pattern_index) CK(cudaMemcpy(pattern_index, d_pat, (size_t)W * 8, cudaMemcpyDeviceToHost));
+    }
+    if (flags & PCSF_TRACKS_BLS) CK(cudaMemcpy(bls, d_bls, (size_t)L * 8, cudaMemcpyDeviceToHost));
+    return PCSF_OK;
+}
+
+// ---- score-msa -------------------------------------------------------------------------------------
+extern "C" pcsf_status pcsf_score_msa(pcsf_model *m, pcsf_strategy strategy, int32_t n_aln, const uint8_t *seqs,
+                                      const int64_t *offset, const int64_t *len, float *phylo, float *anc, float *bls) {
+    if (!m || n_aln < 0 || (n_aln > 0 && (!seqs || !offset || !len)))
+        return fail(PCSF_ERR_INVALID, "pcsf_score_msa: bad argument");
+    if (strategy != PCSF_STRATEGY_FIXED && strategy != PCSF_STRATEGY_MLE)
+        return fail(PCSF_ERR_INVALID, "pcsf_score_msa: unknown strategy");
+    CK(cudaSetDevice(m->device));
+    if (n_aln == 0) return PCSF_OK;
+    const int nl = m->host.nl;
+    cudaStream_t st = nullptr;
+    // concatenate the alignments along the columns into one [nl][Ltot] matrix (2 pad columns between them)
+    std::vector<int64_t> col_start(n_aln), win_start(n_aln), lens(len, len + n_aln);
+    int64_t Ltot = 0, nwin = 0;
+    for (int i = 0; i < n_aln; ++i) {
+        if (len[i] < 0) return fail(PCSF_ERR_INVALID, "negative alignment length");
+        col_start[i] = Ltot; win_start[i] = nwin;
+        Ltot += len[i] + 2; nwin += len[i] / 3;
+    }
+    if (Ltot >= ((int64_t)1 << 32) || nwin >= ((int64_t)1 << 31))
+        return fail(PCSF_ERR_INVALID, "batch too large: split the call");
+    const int64_t ldd = ((Ltot + 15) / 16) * 16;
+    std::vector<uint8_t> h((size_t)ldd * nl, (uint8_t)'N');
+    for (int i = 0; i < n_aln; ++i)
+        for (int s = 0; s < nl; ++s)
+            memcpy(h.data() + (size_t)s * ldd + col_start[i], seqs + offset[i] + (size_t)s * len[i], (size_t)len[i]);
+    std::vector<uint32_t> win_off((size_t)std::max<int64_t>(nwin, 1));
+    for (int i = 0; i < n_aln; ++i)
+        for (int64_t k = 0; k < len[i] / 3; ++k) win_off[win_start[i] + k] = (uint32_t)(col_start[i] + 3 * k);
+    CK(m->io_in.reserve(h.size()));
+    CK(cudaMemcpyAsync(m->io_in.p, h.data(), h.size(), cudaMemcpyHostToDevice, st));
+    pcsf_status rc;
+    if ((rc = run_pack(m, m->io_in.as<uint8_t>(), Ltot, ldd, st))) return rc;
+    // misc: win_off | col_start | win_start | len | outputs
+    const size_t o_win = 0, o_cs = o_win + ((win_off.size() * 4 + 15) / 16) * 16, o_ws = o_cs + (size_t)n_aln * 8,
+                 o_len = o_ws + (size_t)n_aln * 8, o_out = o_len + (size_t)n_aln * 8, total = o_out + (size_t)n_aln * 12 + 64;
+    CK(m->misc.reserve(total));
+    unsigned char *mb = m->misc.as<unsigned char>();
+    CK(cudaMemcpyAsync(mb + o_win, win_off.data(), win_off.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(mb + o_cs, col_start.data(), (size_t)n_aln * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(mb + o_ws, win_start.data(), (size_t)n_aln * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(mb + o_len, lens.data(), (size_t)n_aln * 8, cudaMemcpyHostToDevice, st));
+    float *d_phylo = reinterpret_cast<float *>(mb + o_out), *d_anc = d_phylo + n_aln, *d_bls = d_anc + n_aln;
+    CK(m->io_out.reserve((size_t)Ltot * 8 + 64));
+    double *d_blraw = m->io_out.as<double>();
+    if (bls) {
+        if ((rc = run_bls(m, Ltot, 1, d_blraw, st))) return rc;
+    }
+    WinSpace ws{m->codes.as<uint8_t>(), m->codes_ld, nl, 1, 0, reinterpret_cast<const uint32_t *>(mb + o_win)};
+    if (strategy == PCSF_STRATEGY_FIXED) {
+        CK(m->perwin.reserve((size_t)std::max<int64_t>(nwin, 1) * 32));
+        if (nwin > 0) {
+            float t0 = 0, t1 = 0, t2 = 0;
+            if ((rc = dedup_and_prune(m, ws, (uint32_t)nwin, true, anc != nullptr, m->d_nuniq, nullptr, 0, st, &t0, &t1, &t2)))
+                return rc;
+            k_scatter_list<<<(unsigned)((nwin + 255) / 256), 256, 0, st>>>(
+                (uint32_t)nwin, m->pidx.as<uint32_t>(), m->logz.as<double>(), m->logz.as<double>() + nwin,
+                anc ? m->anc.as<double>() : nullptr, anc ? m->anc.as<double>() + nwin : nullptr, m->perwin.as<double>());
+            CK(cudaGetLastError());
+        }
+        k_aln_sums<<<(n_aln + 127) / 128, 128, 0, st>>>(n_aln, reinterpret_cast<const int64_t *>(mb + o_ws),
+                                                       reinterpret_cast<const int64_t *>(mb + o_cs),
+                                                       reinterpret_cast<const int64_t *>(mb + o_len), m->perwin.as<double>(),
+                                                       nwin, d_blraw, m->host.bls_all, phylo ? d_phylo : nullptr,
+                                                       anc ? d_anc : nullptr, bls ? d_bls : nullptr);
+        CK(cudaGetLastError());
+    } else {
+        MleBatch b{};
+        b.n_aln = n_aln;
+        b.d_win_start = reinterpret_cast<const int64_t *>(mb + o_ws);
+        b.d_col_start = reinterpret_cast<const int64_t *>(mb + o_cs);
+        b.d_len = reinterpret_cast<const int64_t *>(mb + o_len);
+        b.ws = ws;
+        b.nwin = nwin;
+        b.want_anc = anc != nullptr;
+        b.d_phylo = phylo ? d_phylo : nullptr;
+        b.d_anc = anc ? d_anc : nullptr;
+        if ((rc = mle_run(m->host, b, m->d_eig, m->d_bl, m->d_program, m->d_gemm_edges, m->mle, m->sm_count, st, g_err)))
+            return rc;
+        // BLS for MLE uses the same per-alignment sum kernel with phylo/anc disabled
+        if (bls) {
+            CK(m->perwin.reserve(64));
+            k_aln_sums<<<(n_aln + 127) / 128, 128, 0, st>>>(n_aln, reinterpret_cast<const int64_t *>(mb + o_ws),
+                                                           reinterpret_cast<const int64_t *>(mb + o_cs),
+                                                           reinterpret_cast<const int64_t *>(mb + o_len), m->perwin.as<double>(),
+                                                           0, d_blraw, m->host.bls_all, nullptr, nullptr, d_bls);
+            CK(cudaGetLastError());
+        }
+    }
+    CK(cudaStreamSynchronize(st));
+    int bad = 0;
+    CK(cudaMemcpy(&bad, m->d_bad, sizeof(int), cudaMemcpyDeviceToHost));
+    if (bad) return fail(PCSF_ERR_BAD_CHAR, "alignment contains a character outside ACGTacgt.-Nn (reference: exit(37))");
+    if (phylo) CK(cudaMemcpy(phylo, d_phylo, (size_t)n_aln * 4, cudaMemcpyDeviceToHost));
+    if (anc) CK(cudaMemcpy(anc, d_anc, (size_t)n_aln * 4, cudaMemcpyDeviceToHost));
+    if (bls) CK(cudaMemcpy(bls, d_bls, (size_t)n_aln * 4, cudaMemcpyDeviceToHost));
+    return PCSF_OK;
+}

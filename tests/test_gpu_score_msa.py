@@ -1,0 +1,59 @@
+"""Parity of the CUDA score-msa path (pcsf_score_msa) against the reference's golden .scores files."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from phylocsfpp_b200 import capi
+from phylocsfpp_b200.maf import MafReader
+from phylocsfpp_b200.models import load_model
+from tests.util import random_alignment
+
+pytestmark = pytest.mark.gpu
+
+
+def golden_rows(path):
+    rows = [ln.rstrip("\n").split("\t") for ln in open(path)]
+    return rows[1:]
+
+
+@pytest.mark.parametrize("maf,scores", [("chr22.50alignments.maf", "chr22.50alignments.fixed.scores"),
+                                        ("chr22.516alignments.maf.gz", "chr22.516alignments.maf.fixed.scores")])
+def test_fixed_golden(golden_dir, maf, scores):
+    """Config 2: score-msa --strategy fixed --comp-anc 1 with 100vertebrates (test/tests.sh:35-37)."""
+    G = os.path.join(golden_dir, "score-msa")
+    model = load_model("100vertebrates")
+    alns = list(MafReader(os.path.join(G, maf), model.seqid_to_phyloid, model.nl, False, warn=False))
+    gold = golden_rows(os.path.join(G, scores))
+    assert len(alns) == len(gold)
+    dm = capi.DeviceModel(model)
+    phylo, anc, bls = dm.score_msa([a.seqs for a in alns], capi.STRATEGY_FIXED)
+    mism = 0
+    for a, g, p, an, b in zip(alns, gold, phylo, anc, bls):
+        # older golden files have no strand column
+        vals = g[4:] if len(g) == 7 else g[3:]
+        assert g[0] == a.chrom and int(g[1]) == a.start_pos and int(g[2]) == a.start_pos + a.L - 1
+        ours = ["%.6f" % p, "%.6f" % an, "%.6f" % b]
+        assert ours[2] == vals[2], "BLS must be exact"
+        for x, y in zip(ours[:2], vals[:2]):
+            assert abs(float(x) - float(y)) <= 1e-3 * max(1.0, abs(float(y)) * 1e-3)
+            mism += x != y
+    print(f"{scores}: {mism} printed values differ in the last digit")
+    assert mism <= len(gold) // 50
+    dm.close()
+
+
+def test_fixed_vs_oracle_random():
+    model = load_model("29mammals")
+    dm = capi.DeviceModel(model)
+    alns = [random_alignment(model.nl, L, seed=100 + L) for L in (0, 1, 2, 3, 5, 30, 31, 32, 299, 300, 1201)]
+    phylo, anc, bls = dm.score_msa(alns, capi.STRATEGY_FIXED)
+    mc = orc.OracleModel(model.tree, model.S_c, model.f_c)
+    mnc = orc.OracleModel(model.tree, model.S_nc, model.f_nc)
+    for a, p, an, b in zip(alns, phylo, anc, bls):
+        rp, ra = orc.run_fixed(mc, mnc, orc.translate(a), True)
+        assert abs(float(p) - float(rp)) <= 1e-3 and abs(float(an) - float(ra)) <= 1e-3
+        if a.shape[1] > 0:
+            assert np.float32(orc.bls(model.tree, a, per_base=False)[0]) == b
+    dm.close()

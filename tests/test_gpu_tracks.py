@@ -1,0 +1,170 @@
+"""Parity of the CUDA build-tracks path (pcsf_tracks, through the C-ABI) against the CPU oracle.
+
+Tolerance (BASELINE.json north_star): |delta| <= 1e-3 decibans on scores; the FP64 path is asserted at
+1e-6 here.  BLS/power, pattern indices and wig positions are bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from phylocsfpp_b200 import capi, tracks
+from phylocsfpp_b200.maf import MafReader
+from phylocsfpp_b200.models import load_model
+from tests.util import pattern_index_reference, random_alignment, read_lines
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-6  # decibans; the contract is 1e-3
+
+
+def oracle_tracks(model, seqs):
+    mc = orc.OracleModel(model.tree, model.S_c, model.f_c)
+    mnc = orc.OracleModel(model.tree, model.S_nc, model.f_nc)
+    plus, minus = orc.window_codons(seqs)
+    return orc.run_tracks(mc, mnc, plus), orc.run_tracks(mc, mnc, minus), orc.bls(model.tree, seqs)[1], plus, minus
+
+
+@pytest.mark.parametrize("name,L", [("7yeast", 64), ("12flies", 333), ("20flies", 200), ("29mammals", 400),
+                                    ("58mammals", 300), ("100vertebrates", 200), ("49birds", 150)])
+def test_tracks_vs_oracle(name, L):
+    model = load_model(name)
+    seqs = random_alignment(model.nl, L, seed=len(name) * 1000 + L)
+    dm = capi.DeviceModel(model)
+    res = dm.tracks(seqs, want_patterns=True)
+    ref_p, ref_m, ref_b, plus, minus = oracle_tracks(model, seqs)
+    assert np.abs(res["plus"] - ref_p).max() <= TOL
+    assert np.abs(res["minus"] - ref_m).max() <= TOL
+    assert np.array_equal(res["bls"], ref_b), "BLS must be bit-exact"
+    assert np.array_equal(res["pattern_index"], pattern_index_reference(plus, minus, 1 << 22))
+    assert res["stats"]["n_windows"] == 2 * (L - 2)
+    assert res["stats"]["n_unique"] == int(res["pattern_index"].max()) + 1
+    dm.close()
+
+
+def test_model_matrices_match_oracle():
+    model = load_model("58mammals")
+    dm = capi.DeviceModel(model)
+    for which, (S, f) in enumerate([(model.S_c, model.f_c), (model.S_nc, model.f_nc)]):
+        lam, pi, P = dm.get(which)
+        om = orc.OracleModel(model.tree, S, f)
+        _, _, _, opi = om.eigen()
+        assert np.abs(pi - opi).max() < 1e-14
+        assert np.abs(P - om.pmatrices()).max() < 1e-12
+    dm.close()
+
+
+def test_reduced_tree_and_external_model(golden_dir):
+    model = load_model("29mammals", "Human,Chimp,Mouse,Dog,Cow,Horse,Elephant,Armadillo,Rat,Rabbit,Cat,Megabat")
+    assert model.nl == 12
+    seqs = random_alignment(model.nl, 500, seed=5)
+    dm = capi.DeviceModel(model)
+    res = dm.tracks(seqs)
+    ref_p, ref_m, ref_b, _, _ = oracle_tracks(model, seqs)
+    assert np.abs(res["plus"] - ref_p).max() <= TOL and np.abs(res["minus"] - ref_m).max() <= TOL
+    assert np.array_equal(res["bls"], ref_b)
+    dm.close()
+    ext = load_model(os.path.join(golden_dir, "build-tracks", "53birds"))
+    builtin = load_model("53birds")
+    assert np.array_equal(ext.S_c, builtin.S_c) and np.array_equal(ext.tree.branch_len, builtin.tree.branch_len)
+
+
+def test_dedup_and_chunking_do_not_change_results():
+    model = load_model("29mammals")
+    seqs = random_alignment(model.nl, 5000, seed=11, gap=0.5, conserve=0.97)
+    dm = capi.DeviceModel(model)
+    a = dm.tracks(seqs, want_patterns=True)
+    b = dm.tracks(seqs, dedup=False)
+    assert a["stats"]["n_unique"] < a["stats"]["n_windows"], "this input must contain repeated site patterns"
+    assert b["stats"]["n_unique"] == b["stats"]["n_windows"]
+    assert np.array_equal(a["plus"], b["plus"]) and np.array_equal(a["minus"], b["minus"])
+    dm.set_chunk_columns(700)
+    c = dm.tracks(seqs, want_patterns=True)
+    assert c["stats"]["n_chunks"] == -(-(5000 - 2) // 700)
+    assert np.array_equal(a["plus"], c["plus"]) and np.array_equal(a["minus"], c["minus"])
+    plus, minus = orc.window_codons(seqs)
+    assert np.array_equal(c["pattern_index"], pattern_index_reference(plus, minus, 700))
+    assert np.array_equal(a["pattern_index"], pattern_index_reference(plus, minus, 1 << 22))
+    dm.close()
+
+
+def test_edge_cases():
+    model = load_model("12flies")
+    dm = capi.DeviceModel(model)
+    for L in (0, 1, 2, 3, 4, 63, 64, 65):
+        seqs = random_alignment(model.nl, L, seed=L)
+        res = dm.tracks(seqs)
+        assert len(res["plus"]) == max(L - 2, 0) and len(res["bls"]) == L
+        if L >= 3:
+            ref_p, ref_m, ref_b, _, _ = oracle_tracks(model, seqs)
+            assert np.abs(res["plus"] - ref_p).max() <= TOL and np.abs(res["minus"] - ref_m).max() <= TOL
+            assert np.array_equal(res["bls"], ref_b)
+    # all-gap / all-N columns: every leaf marginalised, score = 10*(log zC - log zNC)/ln10 of the row-sum products
+    seqs = np.full((model.nl, 30), ord("-"), np.uint8)
+    seqs[:, 10:20] = ord("N")
+    res = dm.tracks(seqs)
+    ref_p, ref_m, ref_b, _, _ = oracle_tracks(model, seqs)
+    assert np.abs(res["plus"] - ref_p).max() <= TOL and np.all(res["bls"] == 0.0)
+    assert res["stats"]["n_unique"] == 1
+    # only one species present -> BLS 0 (additional_scores.hpp:66-79)
+    seqs[0, :] = ord("A")
+    assert np.all(dm.tracks(seqs)["bls"] == 0.0)
+    # a character outside ACGTacgt.-Nn: the reference exit(37)s
+    seqs[3, 7] = ord("R")
+    with pytest.raises(capi.PcsfError) as ei:
+        dm.tracks(seqs)
+    assert ei.value.status == capi.PCSF_ERR_BAD_CHAR
+    dm.close()
+
+
+def test_reverse_complement_symmetry_large():
+    """Size-independent property at a BASELINE-scale model: the '-' track of S equals the '+' track of
+    revcomp(S) read backwards (build_tracks.hpp:175-226), and BLS reverses."""
+    model = load_model("58mammals")
+    L = 200_000
+    seqs = random_alignment(model.nl, L, seed=3, gap=0.3, conserve=0.9)
+    dm = capi.DeviceModel(model)
+    a = dm.tracks(seqs)
+    b = dm.tracks(orc.reverse_complement(seqs))
+    assert np.array_equal(a["minus"], b["plus"][::-1])
+    assert np.array_equal(a["plus"], b["minus"][::-1])
+    assert np.array_equal(a["bls"], b["bls"][::-1])
+    # spot-check 64 windows against the oracle
+    idx = np.random.default_rng(0).integers(0, L - 2, 64)
+    mc = orc.OracleModel(model.tree, model.S_c, model.f_c)
+    mnc = orc.OracleModel(model.tree, model.S_nc, model.f_nc)
+    sub = np.stack([seqs[:, i:i + 3] for i in idx], axis=1).reshape(model.nl, -1)
+    ref = orc.run_tracks(mc, mnc, orc.translate(sub))
+    assert np.abs(a["plus"][idx] - ref).max() <= TOL
+    dm.close()
+
+
+def test_build_tracks_golden(golden_dir):
+    """Config 1: the reference's own expected wig files (test/tests.sh:15-19), external 53birds model."""
+    G = os.path.join(golden_dir, "build-tracks")
+    model = load_model(os.path.join(G, "53birds"))
+    dm = capi.DeviceModel(model)
+    out = {k: [] for k in tracks.FRAMES}
+    power = []
+    for aln in MafReader(os.path.join(G, "galGal6_chr22_25_28_each_30k_bases.maf.gz"), model.seqid_to_phyloid, model.nl,
+                         True, warn=False):
+        res = dm.tracks(aln.seqs)
+        power += tracks.power_wig(aln.chrom, aln.start_pos, res["bls"])
+        r = tracks.raw_wigs(aln.chrom, aln.start_pos, aln.chrom_len, res["plus"], res["minus"], res["bls"])
+        for k in out:
+            out[k] += r[k]
+    assert power == read_lines(os.path.join(G, "PhyloCSFpower.wig.gz")), "power track must be byte-identical"
+    flips = 0
+    for (s, f), lines in out.items():
+        gold = read_lines(os.path.join(G, tracks.wig_filename(s, f) + ".gz"))
+        assert len(lines) == len(gold)
+        for x, y in zip(lines, gold):
+            if x == y:
+                continue
+            assert not y.startswith("fixedStep") and not x.startswith("fixedStep"), "wig positions must be exact"
+            assert abs(float(x) - float(y)) <= 1e-3 + 1e-9
+            flips += 1
+    print(f"build-tracks golden: {flips} printed digits differ (FP64 path expects 0)")
+    assert flips == 0
+    dm.close()

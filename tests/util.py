@@ -1,0 +1,58 @@
+"""Shared helpers for the parity tests."""
+from __future__ import annotations
+
+import gzip
+import os
+
+import numpy as np
+
+ALPHABET = np.frombuffer(b"ACGTacgtN-.n", np.uint8)
+
+
+def random_alignment(nl: int, L: int, seed: int, gap: float = 0.3, conserve: float = 0.7) -> np.ndarray:
+    """Random ASCII alignment [nl, L]: a random ancestral row copied to every species with per-cell mutation
+    (1 - conserve), upper/lower case mix, and `gap` of the cells replaced by one of N - . n."""
+    rng = np.random.default_rng(seed)
+    anc = rng.integers(0, 4, size=L)
+    cells = np.where(rng.random((nl, L)) < conserve, anc[None, :], rng.integers(0, 4, size=(nl, L)))
+    lower = rng.random((nl, L)) < 0.3
+    out = ALPHABET[cells + 4 * lower]
+    miss = rng.random((nl, L)) < gap
+    out = np.where(miss, ALPHABET[8 + rng.integers(0, 4, size=(nl, L))], out)
+    return np.ascontiguousarray(out, np.uint8)
+
+
+def read_lines(path: str):
+    opener = gzip.open if path.endswith(".gz") else open
+    with opener(path, "rt") as fh:
+        lines = fh.read().split("\n")
+    if lines and lines[-1] == "":
+        lines.pop()
+    return lines
+
+
+def first_occurrence_ranks(keys) -> np.ndarray:
+    """CPU restatement of the site-pattern index rule: rank of the first occurrence of each key, in order."""
+    seen = {}
+    out = np.zeros(len(keys), np.uint32)
+    for i, k in enumerate(keys):
+        r = seen.get(k)
+        if r is None:
+            r = len(seen)
+            seen[k] = r
+        out[i] = r
+    return out
+
+
+def pattern_index_reference(plus: np.ndarray, minus: np.ndarray, chunk_cols: int) -> np.ndarray:
+    """pattern_index[2*o + strand] for codon-id matrices plus/minus [nl, W], dedup domain = chunk of columns."""
+    nl, W = plus.shape
+    out = np.zeros(2 * W, np.uint32)
+    for c0 in range(0, W, chunk_cols):
+        c1 = min(W, c0 + chunk_cols)
+        keys = []
+        for o in range(c0, c1):
+            keys.append(plus[:, o].tobytes())
+            keys.append(minus[:, o].tobytes())
+        out[2 * c0:2 * c1] = first_occurrence_ranks(keys)
+    return out

@@ -84,6 +84,7 @@ typedef struct {
     int64_t n_windows;        /* 2 * max(L-2, 0) */
     int64_t n_unique;         /* prunings actually executed per model (after site-pattern dedup) */
     int32_t n_chunks;         /* dedup domains */
+    int32_t n_launches;       /* kernels launched by the call */
     float ms_pack, ms_hash, ms_dedup, ms_prune, ms_scatter, ms_bls; /* device times (CUDA events); 0 unless timing enabled */
 } pcsf_tracks_stats;
 

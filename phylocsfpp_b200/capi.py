@@ -49,7 +49,7 @@ class ModelDesc(C.Structure):
 
 
 class TracksStats(C.Structure):
-    _fields_ = [("n_windows", C.c_int64), ("n_unique", C.c_int64), ("n_chunks", C.c_int32),
+    _fields_ = [("n_windows", C.c_int64), ("n_unique", C.c_int64), ("n_chunks", C.c_int32), ("n_launches", C.c_int32),
                 ("ms_pack", C.c_float), ("ms_hash", C.c_float), ("ms_dedup", C.c_float), ("ms_prune", C.c_float),
                 ("ms_scatter", C.c_float), ("ms_bls", C.c_float)]
 

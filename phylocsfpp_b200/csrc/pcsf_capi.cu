@@ -65,6 +65,7 @@ struct pcsf_model {
     bool timing = false;
     pcsf_tracks_stats last{};
     int64_t last_nwin = 0;
+    int launches = 0;
     int last_chunks = 0;
     int64_t codes_ld = 0;
     size_t prune_smem = 0;
@@ -208,10 +209,10 @@ static pcsf_status dedup_and_prune(pcsf_model *m, const WinSpace &ws, uint32_t n
         CK(m->khi.reserve((size_t)nwin * 8));
         if (ws.mode == 0) {
             const int64_t ncols = nwin / 2;
-            k_keys_tracks<<<(unsigned)((ncols + TB - 1) / TB), TB, 0, st>>>(ws, ncols, m->klo.as<ulonglong2>(),
+            m->launches++; k_keys_tracks<<<(unsigned)((ncols + TB - 1) / TB), TB, 0, st>>>(ws, ncols, m->klo.as<ulonglong2>(),
                                                                            m->khi.as<ulonglong2>());
         } else {
-            k_keys_list<<<nblk, TB, 0, st>>>(ws, nwin, m->klo.as<uint64_t>(), m->khi.as<uint64_t>());
+            m->launches++; k_keys_list<<<nblk, TB, 0, st>>>(ws, nwin, m->klo.as<uint64_t>(), m->khi.as<uint64_t>());
         }
         CK(cudaGetLastError());
         if (m->timing) CK(cudaEventRecord(m->ev[1], st));
@@ -224,7 +225,7 @@ static pcsf_status dedup_and_prune(pcsf_model *m, const WinSpace &ws, uint32_t n
         CK(m->bsums.reserve((size_t)(nsb + 1) * 4));
         CK(cudaMemsetAsync(m->table.p, 0xFF, (size_t)T * 4, st));
         CK(cudaMemsetAsync(m->slotmin.p, 0xFF, (size_t)T * 4, st));
-        k_insert<<<nblk, TB, 0, st>>>(m->klo.as<uint64_t>(), m->khi.as<uint64_t>(), nwin, m->table.as<uint32_t>(), T - 1,
+        m->launches += 5; k_insert<<<nblk, TB, 0, st>>>(m->klo.as<uint64_t>(), m->khi.as<uint64_t>(), nwin, m->table.as<uint32_t>(), T - 1,
                                       m->slot.as<uint32_t>(), m->slotmin.as<uint32_t>());
         k_resolve<<<nblk, TB, 0, st>>>(nwin, m->slot.as<uint32_t>(), m->slotmin.as<uint32_t>(), m->flag.as<uint32_t>());
         k_scan_blocks<<<nsb, SCAN_THREADS, 0, st>>>(m->flag.as<uint32_t>(), nwin, m->bsums.as<uint32_t>());
@@ -234,7 +235,7 @@ static pcsf_status dedup_and_prune(pcsf_model *m, const WinSpace &ws, uint32_t n
         CK(cudaGetLastError());
     } else {
         if (m->timing) CK(cudaEventRecord(m->ev[1], st));
-        k_identity<<<nblk, TB, 0, st>>>(nwin, m->uniq.as<uint32_t>(), m->pidx.as<uint32_t>(), d_nuniq_slot, d_pattern_out,
+        m->launches++; k_identity<<<nblk, TB, 0, st>>>(nwin, m->uniq.as<uint32_t>(), m->pidx.as<uint32_t>(), d_nuniq_slot, d_pattern_out,
                                         out_base);
         CK(cudaGetLastError());
     }
@@ -257,7 +258,7 @@ static pcsf_status dedup_and_prune(pcsf_model *m, const WinSpace &ws, uint32_t n
     }
     const uint32_t max_tiles = (nwin + PR_TILE_W - 1) / PR_TILE_W;
     const unsigned grid = std::min<uint32_t>((uint32_t)m->sm_count, std::max<uint32_t>(1u, max_tiles));
-    k_prune<<<grid, PR_THREADS, m->prune_smem, st>>>(pa);
+    m->launches++; k_prune<<<grid, PR_THREADS, m->prune_smem, st>>>(pa);
     CK(cudaGetLastError());
     if (m->timing) {
         CK(cudaEventRecord(m->ev[3], st));
@@ -277,7 +278,7 @@ static pcsf_status run_pack(pcsf_model *m, const uint8_t *d_seqs, int64_t L, int
     CK(cudaMemsetAsync(m->d_bad, 0, sizeof(int), st));
     const int64_t nvec = m->codes_ld / 16;
     dim3 grid((unsigned)std::min<int64_t>((nvec + 255) / 256, 65535), nl);
-    k_pack<<<grid, 256, 0, st>>>(d_seqs, L, ld, nl, m->codes.as<uint8_t>(), m->codes_ld, m->d_bad);
+    m->launches++; k_pack<<<grid, 256, 0, st>>>(d_seqs, L, ld, nl, m->codes.as<uint8_t>(), m->codes_ld, m->d_bad);
     CK(cudaGetLastError());
     return PCSF_OK;
 }
@@ -285,7 +286,7 @@ static pcsf_status run_pack(pcsf_model *m, const uint8_t *d_seqs, int64_t L, int
 static pcsf_status run_bls(pcsf_model *m, int64_t L, int raw, double *d_out, cudaStream_t st) {
     if (L <= 0) return PCSF_OK;
     const size_t sh = (size_t)std::max(1, m->host.bls_depth) * BLS_THREADS * 8;
-    k_bls<<<(unsigned)((L + BLS_THREADS - 1) / BLS_THREADS), BLS_THREADS, sh, st>>>(
+    m->launches++; k_bls<<<(unsigned)((L + BLS_THREADS - 1) / BLS_THREADS), BLS_THREADS, sh, st>>>(
         m->codes.as<uint8_t>(), m->codes_ld, m->host.nl, L, m->d_bls_prog, (int)m->host.bls_prog.size(),
         m->host.bls_depth, m->host.bls_all, raw, d_out);
     CK(cudaGetLastError());
@@ -304,6 +305,7 @@ extern "C" pcsf_status pcsf_tracks_device(pcsf_model *m, const uint8_t *d_seqs, 
     m->last = pcsf_tracks_stats{};
     m->last_nwin = 0;
     m->last_chunks = 0;
+    m->launches = 0;
     if (L == 0) return PCSF_OK;
     pcsf_status rc;
     if (m->timing) CK(cudaEventRecord(m->ev[4], st));
@@ -330,7 +332,7 @@ extern "C" pcsf_status pcsf_tracks_device(pcsf_model *m, const uint8_t *d_seqs, 
                                       2 * c0, st, &m->last.ms_hash, &m->last.ms_dedup, &m->last.ms_prune)))
                 return rc;
             if (m->timing) CK(cudaEventRecord(m->ev[0], st));
-            k_scatter_tracks<<<(nwin + 255) / 256, 256, 0, st>>>(nwin, m->pidx.as<uint32_t>(), m->logz.as<double>(),
+            m->launches++; k_scatter_tracks<<<(nwin + 255) / 256, 256, 0, st>>>(nwin, m->pidx.as<uint32_t>(), m->logz.as<double>(),
                                                                  m->logz.as<double>() + nwin, c0, d_plus, d_minus);
             CK(cudaGetLastError());
             if (m->timing) {
@@ -356,6 +358,7 @@ extern "C" pcsf_status pcsf_tracks_device_finish(pcsf_model *m, void *cuda_strea
     CK(cudaMemcpy(&bad, m->d_bad, sizeof(int), cudaMemcpyDeviceToHost));
     m->last.n_windows = m->last_nwin;
     m->last.n_chunks = m->last_chunks;
+    m->last.n_launches = m->launches;
     m->last.n_unique = 0;
     if (m->last_chunks > 0) {
         std::vector<uint32_t> nu(m->last_chunks);

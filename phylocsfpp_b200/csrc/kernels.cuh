@@ -314,8 +314,20 @@ constexpr int PR_TILE_W = PR_NWARP * 8;     // 64 windows per CTA pass
 constexpr int PR_NSTAGE = 2;
 constexpr int PR_TILE_BYTES = NS * NS * 8;  // 32 KB
 
+// Per-tile descriptor (MLE): every alignment has its own P(rho) stream during the Brent search.
+struct TileDesc {
+    const double *pstream;   // [n_gemm][4096] of this tile's (alignment, model)
+    const double *leafPT;    // [nl][65][64]
+    int32_t model;           // 0 coding / 1 non-coding (selects pi)
+    int32_t count;           // windows in this tile (<= 64)
+    uint32_t win0;           // first window (index into ws.win_off) == output index
+    uint32_t pad;
+};
+
 struct PruneArgs {
     WinSpace ws;
+    const TileDesc *tiles;       // per-tile mode only
+    const uint32_t *n_tiles;     // per-tile mode only (device scalar)
     const uint32_t *uniq;        // [n_unique] local window ids
     const uint32_t *n_unique;    // device scalar
     const int32_t *program;
@@ -338,6 +350,7 @@ __host__ __device__ inline size_t prune_smem_bytes(int nl, int n_ops, int max_st
     return b;
 }
 
+template <bool PER_TILE>
 __global__ void __launch_bounds__(PR_THREADS, 1) k_prune(const PruneArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *sp_ = smem;
@@ -361,22 +374,24 @@ __global__ void __launch_bounds__(PR_THREADS, 1) k_prune(const PruneArgs a) {
     }
     __syncthreads();
 
-    const uint32_t n_unique = *a.n_unique;
-    const uint32_t ntiles = (n_unique + PR_TILE_W - 1) / PR_TILE_W;
+    const uint32_t n_unique = PER_TILE ? 0u : *a.n_unique;
+    const uint32_t ntiles = PER_TILE ? *a.n_tiles : (n_unique + PR_TILE_W - 1) / PR_TILE_W;
+    constexpr int NMODEL = PER_TILE ? 1 : 2;
 
     if (warp == PR_NWARP) {
         // ---- TMA producer: P tiles in program order, for every (tile, model) this CTA processes
         if (lane == 0) {
             uint32_t use = 0;
             for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-                for (int m = 0; m < 2; ++m)
+                for (int m = 0; m < NMODEL; ++m) {
+                    const double *ps = PER_TILE ? a.tiles[tile].pstream : a.pstream[m];
                     for (int g = 0; g < a.n_gemm; ++g, ++use) {
                         const uint32_t st = use % PR_NSTAGE;
                         mbar_wait(empty + st, ((use / PR_NSTAGE) & 1) ^ 1);
                         mbar_arrive_expect_tx(full + st, PR_TILE_BYTES);
-                        tma_bulk_g2s(stage_buf + (size_t)st * NS * NS, a.pstream[m] + (size_t)g * NS * NS,
-                                     PR_TILE_BYTES, full + st);
+                        tma_bulk_g2s(stage_buf + (size_t)st * NS * NS, ps + (size_t)g * NS * NS, PR_TILE_BYTES, full + st);
                     }
+                }
         }
         return;
     }
@@ -388,12 +403,19 @@ __global__ void __launch_bounds__(PR_THREADS, 1) k_prune(const PruneArgs a) {
     uint32_t use = 0;
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         // leaf codon ids of this tile's 64 windows
+        TileDesc td{};
+        if (PER_TILE) td = a.tiles[tile];
         named_bar_sync(1, PR_NWARP * 32);
         for (int i = tid; i < a.ws.nl * PR_TILE_W; i += PR_NWARP * 32) {
             const int s = i / PR_TILE_W, wi = i % PR_TILE_W;
-            uint32_t u = tile * PR_TILE_W + wi;
-            if (u >= n_unique) u = n_unique - 1;
-            const uint32_t lw = a.uniq[u];
+            uint32_t lw;
+            if (PER_TILE) {
+                lw = td.win0 + (uint32_t)(wi < td.count ? wi : td.count - 1);
+            } else {
+                uint32_t u = tile * PR_TILE_W + wi;
+                if (u >= n_unique) u = n_unique - 1;
+                lw = a.uniq[u];
+            }
             int64_t o; uint32_t strand;
             if (a.ws.mode == 0) { o = a.ws.c0 + (lw >> 1); strand = lw & 1; }
             else { o = a.ws.win_off[lw]; strand = 0; }
@@ -403,8 +425,9 @@ __global__ void __launch_bounds__(PR_THREADS, 1) k_prune(const PruneArgs a) {
         }
         named_bar_sync(1, PR_NWARP * 32);
 
-        for (int m = 0; m < 2; ++m) {
-            const double *leafPT = a.leafPT[m];
+        for (int mm = 0; mm < NMODEL; ++mm) {
+            const int m = PER_TILE ? td.model : mm;
+            const double *leafPT = PER_TILE ? td.leafPT : a.leafPT[m];
             double R[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) R[i] = 0.0;
@@ -469,7 +492,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) k_prune(const PruneArgs a) {
                     z += __shfl_xor_sync(0xffffffffu, z, 1);
                     z += __shfl_xor_sync(0xffffffffu, z, 2);
                     double e = 0.0;
-                    if (a.anc[m] != nullptr) {
+                    if (a.anc[PER_TILE ? 0 : m] != nullptr) {
                         if (z != 0.0) {
 #pragma unroll
                             for (int nt = 0; nt < 8; ++nt) {
@@ -480,10 +503,17 @@ __global__ void __launch_bounds__(PR_THREADS, 1) k_prune(const PruneArgs a) {
                         e += __shfl_xor_sync(0xffffffffu, e, 1);
                         e += __shfl_xor_sync(0xffffffffu, e, 2);
                     }
-                    const uint32_t u = tile * PR_TILE_W + mywin;
-                    if (q == 0 && u < n_unique) {
-                        a.logz[m][u] = log(z);
-                        if (a.anc[m] != nullptr) a.anc[m][u] = e;
+                    if (PER_TILE) {
+                        if (q == 0 && mywin < td.count) {
+                            a.logz[0][td.win0 + mywin] = log(z);
+                            if (a.anc[0] != nullptr) a.anc[0][td.win0 + mywin] = e;
+                        }
+                    } else {
+                        const uint32_t u = tile * PR_TILE_W + mywin;
+                        if (q == 0 && u < n_unique) {
+                            a.logz[m][u] = log(z);
+                            if (a.anc[m] != nullptr) a.anc[m][u] = e;
+                        }
                     }
                 }
             }

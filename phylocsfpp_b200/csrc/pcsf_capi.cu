@@ -139,10 +139,10 @@ extern "C" pcsf_status pcsf_model_create(const pcsf_model_desc *d, int device, p
         return fail(PCSF_ERR_UNSUPPORTED, "tree needs more shared memory than one SM has (stack depth " +
                                               std::to_string(m->host.max_stack) + ")");
     }
-    CK(cudaFuncSetAttribute(k_prune, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->prune_smem));
+    CK(cudaFuncSetAttribute(k_prune<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->prune_smem));
+    CK(cudaFuncSetAttribute(k_prune<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->prune_smem));
     CK(cudaFuncSetAttribute(k_bls, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             std::max(1, m->host.bls_depth) * BLS_THREADS * 8));
-    if ((st = mle_setup(m->host))) return fail(st, "mle kernel setup failed");
     *out = m;
     return PCSF_OK;
 }
@@ -258,7 +258,7 @@ static pcsf_status dedup_and_prune(pcsf_model *m, const WinSpace &ws, uint32_t n
     }
     const uint32_t max_tiles = (nwin + PR_TILE_W - 1) / PR_TILE_W;
     const unsigned grid = std::min<uint32_t>((uint32_t)m->sm_count, std::max<uint32_t>(1u, max_tiles));
-    m->launches++; k_prune<<<grid, PR_THREADS, m->prune_smem, st>>>(pa);
+    m->launches++; k_prune<false><<<grid, PR_THREADS, m->prune_smem, st>>>(pa);
     CK(cudaGetLastError());
     if (m->timing) {
         CK(cudaEventRecord(m->ev[3], st));
@@ -475,7 +475,8 @@ extern "C" pcsf_status pcsf_score_msa(pcsf_model *m, pcsf_strategy strategy, int
         b.want_anc = anc != nullptr;
         b.d_phylo = phylo ? d_phylo : nullptr;
         b.d_anc = anc ? d_anc : nullptr;
-        if ((rc = mle_run(m->host, b, m->d_eig, m->d_bl, m->d_program, m->d_gemm_edges, m->mle, m->sm_count, st, g_err)))
+        if ((rc = mle_run(m->host, b, m->d_eig, m->d_bl, m->d_program, m->d_pi, m->d_logpi, m->mle, m->sm_count,
+                          m->prune_smem, st, g_err, &m->launches)))
             return rc;
         // BLS for MLE uses the same per-alignment sum kernel with phylo/anc disabled
         if (bls) {

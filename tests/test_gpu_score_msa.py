@@ -57,3 +57,42 @@ def test_fixed_vs_oracle_random():
         if a.shape[1] > 0:
             assert np.float32(orc.bls(model.tree, a, per_base=False)[0]) == b
     dm.close()
+
+
+def test_mle_golden_small(golden_dir):
+    """score-msa --strategy mle --comp-anc 1, 100vertebrates, against the reference's own output with the
+    reference's own CI tolerance (squared error <= 0.001 per score, test/tests.sh:40-42); most rows agree
+    to 1e-3 (rows that do not are Brent trajectories that fork on ~1e-13 differences in P(t))."""
+    G = os.path.join(golden_dir, "score-msa")
+    model = load_model("100vertebrates")
+    alns = list(MafReader(os.path.join(G, "chr22.50alignments.maf"), model.seqid_to_phyloid, model.nl, False, warn=False))
+    gold = golden_rows(os.path.join(G, "chr22.50alignments.mle.scores"))
+    dm = capi.DeviceModel(model)
+    phylo, anc, bls = dm.score_msa([a.seqs for a in alns], capi.STRATEGY_MLE)
+    tight = 0
+    for a, g, p, an, b in zip(alns, gold, phylo, anc, bls):
+        assert g[0] == a.chrom and int(g[1]) == a.start_pos and int(g[2]) == a.start_pos + a.L - 1
+        assert (float(p) - float(g[4])) ** 2 <= 0.001, (g, p)
+        assert (float(an) - float(g[5])) ** 2 <= 0.001, (g, an)
+        assert "%.6f" % b == g[6]
+        tight += abs(float(p) - float(g[4])) <= 1e-3 and abs(float(an) - float(g[5])) <= 1e-3
+    print(f"MLE golden: {tight}/{len(gold)} rows within 1e-3 of the reference output")
+    assert tight >= 0.8 * len(gold)
+    dm.close()
+
+
+def test_mle_vs_oracle_random():
+    model = load_model("29mammals", "Human,Chimp,Mouse,Dog,Cow,Horse,Elephant,Armadillo,Rat,Rabbit,Cat,Megabat")
+    dm = capi.DeviceModel(model)
+    alns = [random_alignment(model.nl, L, seed=900 + L, gap=0.2, conserve=c)
+            for L, c in ((0, .7), (2, .7), (3, .7), (30, .9), (61, .5), (150, .8), (299, .95), (600, .6), (900, .85))]
+    phylo, anc, bls = dm.score_msa(alns, capi.STRATEGY_MLE)
+    mc = orc.OracleModel(model.tree, model.S_c, model.f_c)
+    mnc = orc.OracleModel(model.tree, model.S_nc, model.f_nc)
+    tight = 0
+    for a, p, an in zip(alns, phylo, anc):
+        rp, ra, info = orc.run_mle(mc, mnc, orc.translate(a), True)
+        assert (float(p) - float(rp)) ** 2 <= 0.001 and (float(an) - float(ra)) ** 2 <= 0.001, (a.shape, p, rp, an, ra, info)
+        tight += abs(float(p) - float(rp)) <= 1e-3 and abs(float(an) - float(ra)) <= 1e-3
+    assert tight >= len(alns) - 1
+    dm.close()

@@ -1,0 +1,46 @@
+"""Multi-GPU sharding of the hot path: independent units, zero exchange.
+
+The reference's only parallelism is an OpenMP loop over MAF byte ranges whose per-job outputs are merged in
+job order (src/phylocsf++build_tracks.hpp:88, :27-53).  Here the unit is one concatenated alignment chain (or one
+score-msa block); ranks get contiguous, column-balanced ranges so that concatenating the per-rank outputs in rank
+order reproduces the single-process output byte for byte.  There is no data-path collective; the only
+communication is the host-side ordered gather of the (small) per-rank results.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+
+def contiguous_partition(weights: Sequence[int], parts: int) -> List[Tuple[int, int]]:
+    """Splits items 0..n-1 into `parts` contiguous ranges [lo, hi) with near-equal total weight (greedy on the
+    cumulative sum; a range may be empty when there are fewer items than parts)."""
+    n = len(weights)
+    total = sum(weights)
+    out, lo, acc = [], 0, 0
+    for p in range(parts):
+        target = total * (p + 1) / parts
+        hi = lo
+        while hi < n and (acc + weights[hi] <= target or (hi == lo and p < parts - 1 and n - hi > parts - 1 - p)):
+            acc += weights[hi]
+            hi += 1
+        if p == parts - 1:
+            hi = n
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+def gather_ordered(obj, dst: int = 0):
+    """Host-side ordered gather: returns [obj_rank0, obj_rank1, ...] on `dst`, None elsewhere.
+    Works with any initialised torch.distributed backend (gloo on CPU, nccl on GPUs); single process -> [obj]."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [obj]
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if dist.get_backend() == "nccl":
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out if rank == dst else None
+    out = [None] * world if rank == dst else None
+    dist.gather_object(obj, out, dst=dst)
+    return out

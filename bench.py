@@ -122,6 +122,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="columns of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dedup", action="store_true")
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"], help="f64: FP64 DMMA path (parity anchor); f32: split-TF32 tensor path")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -185,7 +186,8 @@ def main():
     plus = torch.empty(Wn, dtype=torch.float64, device=dev)
     minus = torch.empty(Wn, dtype=torch.float64, device=dev)
     bls = torch.empty(B, dtype=torch.float64, device=dev)
-    flags = capi.TRACKS_SCORES | capi.TRACKS_BLS | (capi.TRACKS_NO_DEDUP if args.no_dedup else 0)
+    flags = (capi.TRACKS_SCORES | capi.TRACKS_BLS | (capi.TRACKS_NO_DEDUP if args.no_dedup else 0)
+             | (capi.TRACKS_FP32 if args.precision == "f32" else 0))
     stream = torch.cuda.current_stream()
 
     def step():

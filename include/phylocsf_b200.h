@@ -78,7 +78,7 @@ int pcsf_abi_version(void);
 #define PCSF_TRACKS_SCORES   0x1u  /* plus[]/minus[] decibans */
 #define PCSF_TRACKS_BLS      0x2u  /* bls[] */
 #define PCSF_TRACKS_NO_DEDUP 0x4u  /* prune every window, do not deduplicate site patterns */
-#define PCSF_TRACKS_FP32     0x8u  /* reserved for the FP32-class tensor path */
+#define PCSF_TRACKS_FP32     0x8u  /* FP32-class tensor path: split-TF32 MMA + per-window log-scaling (|delta| <= 1e-3 decibans) */
 
 typedef struct {
     int64_t n_windows;        /* 2 * max(L-2, 0) */

@@ -308,9 +308,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // wait in a per-warp shared-memory stack (depth = Strahler number - 1 of the tree).
 // B fragments (the P_c tiles, pre-ordered on the host so a warp's LDS.128 is 512 contiguous bytes) are
 // streamed global -> shared by 1-D bulk TMA in program order through a 2-stage full/empty mbarrier ring.
-constexpr int PR_NWARP = 8;                 // compute warps
-constexpr int PR_THREADS = (PR_NWARP + 1) * 32;
-constexpr int PR_TILE_W = PR_NWARP * 8;     // 64 windows per CTA pass
+constexpr int PR_MAX_NWARP = 12;            // compute warps: 12 (3 per SMSP) when shared memory allows, else 8
+constexpr int PR_THREADS = (PR_MAX_NWARP + 1) * 32;   // launch bound; the launch uses (nwarp + 1) * 32
 constexpr int PR_NSTAGE = 2;
 constexpr int PR_TILE_BYTES = NS * NS * 8;  // 32 KB
 
@@ -319,7 +318,7 @@ struct TileDesc {
     const double *pstream;   // [n_gemm][4096] of this tile's (alignment, model)
     const double *leafPT;    // [nl][65][64]
     int32_t model;           // 0 coding / 1 non-coding (selects pi)
-    int32_t count;           // windows in this tile (<= 64)
+    int32_t count;           // windows in this tile (<= 8 * nwarp)
     uint32_t win0;           // first window (index into ws.win_off) == output index
     uint32_t pad;
 };
@@ -332,18 +331,20 @@ struct PruneArgs {
     const uint32_t *n_unique;    // device scalar
     const int32_t *program;
     int n_ops, n_gemm, max_stack;
+    int nwarp;                   // compute warps per CTA (8 windows each)
     const double *pstream[2];    // [n_gemm][4096] fragment-ordered
     const double *leafPT[2];     // [nl][65][64]
     const double *pi[2];
     const double *logpi[2];
     double *logz[2];             // [capacity]
     double *anc[2];              // nullable
+    uint32_t stagger_ns;         // phase offset between the two warps of an SMSP (see k_prune)
 };
 
-__host__ __device__ inline size_t prune_smem_bytes(int nl, int n_ops, int max_stack) {
+__host__ __device__ inline size_t prune_smem_bytes(int nl, int n_ops, int max_stack, int nwarp) {
     size_t b = (size_t)PR_NSTAGE * PR_TILE_BYTES;            // P stages
-    b += (size_t)PR_NWARP * (max_stack > 0 ? max_stack : 1) * 4096;  // stacks
-    b += (size_t)((nl * PR_TILE_W + 15) / 16) * 16;          // leaf codon ids
+    b += (size_t)nwarp * (max_stack > 0 ? max_stack : 1) * 4096;  // stacks
+    b += (size_t)((nl * nwarp * 8 + 15) / 16) * 16;          // leaf codon ids
     b += (size_t)((n_ops * 4 + 15) / 16) * 16;               // program
     b += 4 * 64 * 8;                                         // pi, logpi x 2 models
     b += 2 * PR_NSTAGE * 8;                                  // mbarriers
@@ -354,6 +355,7 @@ template <bool PER_TILE>
 __global__ void __launch_bounds__(PR_THREADS, 1) k_prune(const PruneArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *sp_ = smem;
+    const int PR_NWARP = a.nwarp, PR_TILE_W = a.nwarp * 8;
     double *stage_buf = reinterpret_cast<double *>(sp_); sp_ += (size_t)PR_NSTAGE * PR_TILE_BYTES;
     double2 *stack = reinterpret_cast<double2 *>(sp_); sp_ += (size_t)PR_NWARP * (a.max_stack > 0 ? a.max_stack : 1) * 4096;
     uint8_t *ids = sp_; sp_ += (size_t)((a.ws.nl * PR_TILE_W + 15) / 16) * 16;
@@ -367,8 +369,8 @@ __global__ void __launch_bounds__(PR_THREADS, 1) k_prune(const PruneArgs a) {
         for (int s = 0; s < PR_NSTAGE; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, PR_NWARP); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < a.n_ops; i += PR_THREADS) prog[i] = a.program[i];
-    for (int i = tid; i < 256; i += PR_THREADS) {
+    for (int i = tid; i < a.n_ops; i += blockDim.x) prog[i] = a.program[i];
+    for (int i = tid; i < 256; i += blockDim.x) {
         const int m = i >> 7, r = i & 127;
         s_pi[i] = r < 64 ? a.pi[m][r] : a.logpi[m][r - 64];
     }
@@ -424,6 +426,10 @@ __global__ void __launch_bounds__(PR_THREADS, 1) k_prune(const PruneArgs a) {
             ids[i] = (uint8_t)(strand ? codon_minus(x0, x1, x2) : codon_plus(x0, x1, x2));
         }
         named_bar_sync(1, PR_NWARP * 32);
+        // Warps w and w+4 share an SMSP and would otherwise run the program in lockstep: both in the DMMA phase,
+        // then both in the gather/stack phase with the tensor pipe idle.  A one-off phase offset per tile makes one
+        // warp's non-DMMA phase overlap the other's DMMA phase.
+        if (warp >= PR_NWARP / 2 && a.stagger_ns) __nanosleep(a.stagger_ns);
 
         for (int mm = 0; mm < NMODEL; ++mm) {
             const int m = PER_TILE ? td.model : mm;

@@ -11,7 +11,7 @@
 //     k_mle_step   consumes the previous evaluation (sequential sums of log z / anc in codon order),
 //                  advances fit_find_init / Brent exactly as the reference does, emits the next rho; a slot
 //                  whose alignment is finished immediately pulls the next alignment from the queue
-//     k_mle_plan   tile descriptors (64 codons each) of every slot with a pending evaluation
+//     k_mle_plan   tile descriptors (one CTA pass of codons each) of every slot with a pending evaluation
 //     k_mle_expm   batched P_b(rho) = S diag(exp(lambda t_b)) S^-1 for every (slot, branch): FP64 DMMA GEMMs,
 //                  the reference's clamp / diagonal / row-sum checks, written straight into the DMMA fragment
 //                  order (inner edges) or the leaf gather tables (leaf edges) that k_prune consumes
@@ -224,7 +224,7 @@ __global__ void k_mle_step(MleSlot *slots, int n_slots, int n_aln, int *queue_he
 
 // Single block: tile descriptors for every slot with a pending evaluation.
 __global__ void __launch_bounds__(1024) k_mle_plan(const MleSlot *__restrict__ slots, int n_slots, const double *pbase,
-                                                    size_t slot_stride /* doubles */, size_t leaf_off /* doubles */,
+                                                    size_t slot_stride /* doubles */, size_t leaf_off /* doubles */, int tw /* windows per tile */,
                                                     TileDesc *__restrict__ tiles, uint32_t *__restrict__ n_tiles) {
     __shared__ uint32_t sh[33];
     const uint32_t per = (n_slots + 1023) / 1024;
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(1024) k_mle_plan(const MleSlot *__restrict__ s
     uint32_t sum = 0;
     for (uint32_t i = 0; i < per; ++i) {
         const uint32_t si = base + i;
-        if (si < (uint32_t)n_slots && slots[si].aln >= 0 && slots[si].pending) sum += (uint32_t)((slots[si].K + 63) / 64);
+        if (si < (uint32_t)n_slots && slots[si].aln >= 0 && slots[si].pending) sum += (uint32_t)((slots[si].K + tw - 1) / tw);
     }
     uint32_t total;
     uint32_t run = block_excl_scan(sum, &total, sh);
@@ -240,14 +240,14 @@ __global__ void __launch_bounds__(1024) k_mle_plan(const MleSlot *__restrict__ s
         const uint32_t si = base + i;
         if (si >= (uint32_t)n_slots || slots[si].aln < 0 || !slots[si].pending) continue;
         const MleSlot &s = slots[si];
-        const uint32_t nt = (uint32_t)((s.K + 63) / 64);
+        const uint32_t nt = (uint32_t)((s.K + tw - 1) / tw);
         for (uint32_t t = 0; t < nt; ++t) {
             TileDesc d;
             d.pstream = pbase + (size_t)si * slot_stride;
             d.leafPT = d.pstream + leaf_off;
             d.model = s.model;
-            { const int64_t rem = s.K - 64 * (int64_t)t; d.count = (int32_t)(rem < 64 ? rem : 64); }
-            d.win0 = (uint32_t)(s.win0 + 64 * (int64_t)t);
+            { const int64_t rem = s.K - tw * (int64_t)t; d.count = (int32_t)(rem < tw ? rem : tw); }
+            d.win0 = (uint32_t)(s.win0 + tw * (int64_t)t);
             d.pad = 0;
             tiles[run + t] = d;
         }
@@ -389,7 +389,7 @@ inline MleSetup mle_prepare(const ModelHost &h, double lo, double hi) {
 template <class Buf>
 inline pcsf_status mle_run(const ModelHost &h, const MleBatch &b, double *const *d_eig, const float *d_bl,
                            const int32_t *d_program, const double *const *d_pi, const double *const *d_logpi, Buf &scratch,
-                           int sm_count, size_t prune_smem, cudaStream_t st, std::string &err, int *launches) {
+                           int sm_count, size_t prune_smem, int prune_nwarp, cudaStream_t st, std::string &err, int *launches) {
     const double lo = 1e-2, hi = 10.0, init = 1.0;   // run.hpp:193-194
     const MleSetup su = mle_prepare(h, lo, hi);
     const int n_br = h.n - 1, n_gemm = (int)h.gemm_edges.size();
@@ -399,7 +399,8 @@ inline pcsf_status mle_run(const ModelHost &h, const MleBatch &b, double *const 
     int n_slots = (int)std::min<size_t>((size_t)b.n_aln, std::max<size_t>(1, budget / (slot_stride * 8)));
     n_slots = std::min(n_slots, 8192);
     const int64_t nwin = std::max<int64_t>(b.nwin, 1);
-    const size_t max_tiles = (size_t)((b.nwin + 63) / 64) + (size_t)b.n_aln + 1;
+    const int tw = prune_nwarp * 8;
+    const size_t max_tiles = (size_t)((b.nwin + tw - 1) / tw) + (size_t)b.n_aln + 1;
 
     // scratch layout
     size_t off = 0;
@@ -433,6 +434,8 @@ inline pcsf_status mle_run(const ModelHost &h, const MleBatch &b, double *const 
     pa.n_ops = (int)h.program.size();
     pa.n_gemm = n_gemm;
     pa.max_stack = h.max_stack;
+    pa.stagger_ns = 0;
+    pa.nwarp = prune_nwarp;
     for (int w = 0; w < 2; ++w) { pa.pi[w] = d_pi[w]; pa.logpi[w] = d_logpi[w]; }
     pa.logz[0] = d_logz;
     pa.anc[0] = b.want_anc ? d_ancw : nullptr;
@@ -450,9 +453,9 @@ inline pcsf_status mle_run(const ModelHost &h, const MleBatch &b, double *const 
         if (launches) *launches += 1;
         if (n_active == 0) return PCSF_OK;
         MCK(cudaMemsetAsync(d_err, 0, (size_t)n_slots * 4, st));
-        k_mle_plan<<<1, 1024, 0, st>>>(d_slots, n_slots, d_p, slot_stride, leaf_off, d_tiles, reinterpret_cast<uint32_t *>(d_ctr + 2));
+        k_mle_plan<<<1, 1024, 0, st>>>(d_slots, n_slots, d_p, slot_stride, leaf_off, tw, d_tiles, reinterpret_cast<uint32_t *>(d_ctr + 2));
         k_mle_expm<<<n_slots * n_br, 128, 0, st>>>(d_slots, n_br, h.nl, d_bl, d_eig[0], d_eig[1], d_e2g, d_p, slot_stride, leaf_off, d_err);
-        k_prune<true><<<sm_count, PR_THREADS, prune_smem, st>>>(pa);
+        k_prune<true><<<sm_count, (prune_nwarp + 1) * 32, prune_smem, st>>>(pa);
         MCK(cudaGetLastError());
         if (launches) *launches += 3;
     }

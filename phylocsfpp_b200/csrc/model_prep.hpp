@@ -42,6 +42,9 @@ struct EcmHost {
     std::vector<double> P;        // (n-1) x 64 x 64 at rho = 1, row-major P[a][b]
     std::vector<double> pstream;  // n_gemm tiles of 4096 doubles, DMMA fragment order, program order
     std::vector<double> leafPT;   // nl x 65 x 64: leafPT[l][x][a] = P_l[a][x], x = 64 -> row sums
+    // FP32-class tensor path (split TF32): tiles of 2048 float4 {hi0, hi1, lo0, lo1}, HMMA.1688 fragment order
+    std::vector<float> pstream32;
+    std::vector<float> leafPT32;  // nl x 65 x 64 floats
 };
 
 struct ModelHost {
@@ -188,6 +191,35 @@ inline void to_fragment_order(const double *P, double *tile) {
                 }
 }
 
+// cvt.rna.tf32.f32 on the host: round to 10 explicit mantissa bits, ties away from zero.
+inline float tf32_rna(float x) {
+    uint32_t u;
+    std::memcpy(&u, &x, 4);
+    u = (u + 0x1000u) & 0xffffe000u;
+    float r;
+    std::memcpy(&r, &u, 4);
+    return r;
+}
+
+// mma.sync.m16n8k8.tf32 B-fragment order of one 64x64 P for the chained, K-permuted GEMM of k_prune_f32:
+//   tile[ks][nt][lane] = float4{hi(P[a][b0]), hi(P[a][b1]), lo(P[a][b0]), lo(P[a][b1])},
+//   a = 8*nt + lane/4, b0 = 8*ks + 2*(lane%4), b1 = b0 + 1; p ~= hi + lo with hi, lo in TF32.
+inline void to_fragment_order_tf32(const double *P, float *tile) {
+    for (int ks = 0; ks < 8; ++ks)
+        for (int nt = 0; nt < 8; ++nt)
+            for (int lane = 0; lane < 32; ++lane) {
+                const int a = 8 * nt + lane / 4, b0 = 8 * ks + 2 * (lane % 4);
+                float *o = tile + ((size_t)(ks * 8 + nt) * 32 + lane) * 4;
+                for (int e = 0; e < 2; ++e) {
+                    const double p = P[a * NS + b0 + e];
+                    const float hi = tf32_rna((float)p);
+                    const float lo = tf32_rna((float)(p - (double)hi));
+                    o[e] = hi;
+                    o[2 + e] = lo;
+                }
+            }
+}
+
 inline void to_leaf_table(const double *P, double *pt /* 65 x 64 */) {
     for (int a = 0; a < NS; ++a) {
         double rs = 0.0;
@@ -330,6 +362,11 @@ inline std::string prepare_model(ModelHost &m, int nl, const int16_t *c1, const 
             to_fragment_order(e.P.data() + (size_t)m.gemm_edges[g] * NS * NS, e.pstream.data() + g * NS * NS);
         e.leafPT.resize((size_t)nl * 65 * NS);
         for (int l = 0; l < nl; ++l) to_leaf_table(e.P.data() + (size_t)l * NS * NS, e.leafPT.data() + (size_t)l * 65 * NS);
+        e.pstream32.resize(m.gemm_edges.size() * (size_t)2 * NS * NS);
+        for (size_t g = 0; g < m.gemm_edges.size(); ++g)
+            to_fragment_order_tf32(e.P.data() + (size_t)m.gemm_edges[g] * NS * NS, e.pstream32.data() + g * 2 * NS * NS);
+        e.leafPT32.resize(e.leafPT.size());
+        for (size_t i = 0; i < e.leafPT.size(); ++i) e.leafPT32[i] = (float)e.leafPT[i];
     }
     return "";
 }

@@ -17,6 +17,7 @@
 
 #include "kernels.cuh"
 #include "mle.cuh"
+#include "prune_f32.cuh"
 
 using namespace pcsf;
 
@@ -53,6 +54,9 @@ struct pcsf_model {
     double *d_pstream[2] = {nullptr, nullptr}, *d_leafPT[2] = {nullptr, nullptr};
     double *d_pi[2] = {nullptr, nullptr}, *d_logpi[2] = {nullptr, nullptr};
     double *d_eig[2] = {nullptr, nullptr};   // lambda[64] | SR[4096] | SRinv[4096]
+    float *d_pstream32[2] = {nullptr, nullptr}, *d_leafPT32[2] = {nullptr, nullptr};
+    size_t prune_f32_smem = 0;
+    int prune_f32_nwarp = 8;
     int32_t *d_program = nullptr;
     BlsNode *d_bls_prog = nullptr;
     float *d_bl = nullptr;
@@ -63,12 +67,14 @@ struct pcsf_model {
     uint32_t *d_nuniq = nullptr;       // [max chunks]
     int64_t chunk_cols = (int64_t)1 << 22;
     bool timing = false;
+    uint32_t stagger_ns = 1000;
     pcsf_tracks_stats last{};
     int64_t last_nwin = 0;
     int launches = 0;
     int last_chunks = 0;
     int64_t codes_ld = 0;
     size_t prune_smem = 0;
+    int prune_nwarp = 8;
     cudaEvent_t ev[8] = {};
 };
 
@@ -101,6 +107,7 @@ extern "C" pcsf_status pcsf_model_create(const pcsf_model_desc *d, int device, p
         return fail(PCSF_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
     }
     m->device = device;
+    if (const char *e = getenv("PCSF_STAGGER_NS")) m->stagger_ns = (uint32_t)atoi(e);
     CK(cudaSetDevice(device));
     CK(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device));
     {
@@ -115,6 +122,8 @@ extern "C" pcsf_status pcsf_model_create(const pcsf_model_desc *d, int device, p
         const EcmHost &e = m->host.ecm[w];
         if ((st = upload(e.pstream.data(), e.pstream.size() * 8, (void **)&m->d_pstream[w]))) return st;
         if ((st = upload(e.leafPT.data(), e.leafPT.size() * 8, (void **)&m->d_leafPT[w]))) return st;
+        if ((st = upload(e.pstream32.data(), e.pstream32.size() * 4, (void **)&m->d_pstream32[w]))) return st;
+        if ((st = upload(e.leafPT32.data(), e.leafPT32.size() * 4, (void **)&m->d_leafPT32[w]))) return st;
         if ((st = upload(e.pi, 64 * 8, (void **)&m->d_pi[w]))) return st;
         if ((st = upload(e.logpi, 64 * 8, (void **)&m->d_logpi[w]))) return st;
         std::vector<double> eig(64 + 2 * 4096);
@@ -134,11 +143,24 @@ extern "C" pcsf_status pcsf_model_create(const pcsf_model_desc *d, int device, p
     CK(cudaMemset(m->d_bad, 0, sizeof(int)));
     CK(cudaMalloc(&m->d_nuniq, sizeof(uint32_t) * MAX_CHUNKS));
     for (auto &e : m->ev) CK(cudaEventCreate(&e));
-    m->prune_smem = prune_smem_bytes(m->host.nl, (int)m->host.program.size(), m->host.max_stack);
+    m->prune_nwarp = PR_MAX_NWARP;
+    if (const char *e = getenv("PCSF_PRUNE_NWARP")) m->prune_nwarp = std::max(1, std::min(PR_MAX_NWARP, atoi(e)));
+    while (m->prune_nwarp > 4 &&
+           prune_smem_bytes(m->host.nl, (int)m->host.program.size(), m->host.max_stack, m->prune_nwarp) > 227 * 1024)
+        m->prune_nwarp -= 4;
+    m->prune_smem = prune_smem_bytes(m->host.nl, (int)m->host.program.size(), m->host.max_stack, m->prune_nwarp);
     if (m->prune_smem > 227 * 1024) {
         return fail(PCSF_ERR_UNSUPPORTED, "tree needs more shared memory than one SM has (stack depth " +
                                               std::to_string(m->host.max_stack) + ")");
     }
+    m->prune_f32_nwarp = PF_MAX_NWARP;
+    if (const char *e = getenv("PCSF_PRUNE_F32_NWARP")) m->prune_f32_nwarp = std::max(1, std::min(PF_MAX_NWARP, atoi(e)));
+    while (m->prune_f32_nwarp > 4 &&
+           prune_f32_smem_bytes(m->host.nl, (int)m->host.program.size(), m->host.max_stack, m->prune_f32_nwarp) > 227 * 1024)
+        m->prune_f32_nwarp -= 2;
+    m->prune_f32_smem = prune_f32_smem_bytes(m->host.nl, (int)m->host.program.size(), m->host.max_stack, m->prune_f32_nwarp);
+    if (m->prune_f32_smem <= 227 * 1024)
+        CK(cudaFuncSetAttribute(k_prune_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->prune_f32_smem));
     CK(cudaFuncSetAttribute(k_prune<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->prune_smem));
     CK(cudaFuncSetAttribute(k_prune<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->prune_smem));
     CK(cudaFuncSetAttribute(k_bls, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -151,7 +173,7 @@ extern "C" void pcsf_model_destroy(pcsf_model *m) {
     if (!m) return;
     cudaSetDevice(m->device);
     for (int w = 0; w < 2; ++w) {
-        cudaFree(m->d_pstream[w]); cudaFree(m->d_leafPT[w]); cudaFree(m->d_pi[w]); cudaFree(m->d_logpi[w]);
+        cudaFree(m->d_pstream[w]); cudaFree(m->d_leafPT[w]); cudaFree(m->d_pstream32[w]); cudaFree(m->d_leafPT32[w]); cudaFree(m->d_pi[w]); cudaFree(m->d_logpi[w]);
         cudaFree(m->d_eig[w]);
     }
     cudaFree(m->d_program); cudaFree(m->d_bls_prog); cudaFree(m->d_bl); cudaFree(m->d_gemm_edges);
@@ -194,7 +216,7 @@ static inline uint32_t next_pow2(uint64_t x) {
 
 // dedup + prune for one window space of `nwin` local windows; results land in m->pidx (pattern id per
 // window), m->logz / m->anc (per pattern); *d_nuniq_slot receives the pattern count.
-static pcsf_status dedup_and_prune(pcsf_model *m, const WinSpace &ws, uint32_t nwin, bool dedup, bool want_anc,
+static pcsf_status dedup_and_prune(pcsf_model *m, const WinSpace &ws, uint32_t nwin, bool dedup, bool want_anc, bool fp32,
                                    uint32_t *d_nuniq_slot, uint32_t *d_pattern_out, int64_t out_base,
                                    cudaStream_t st, float *ms_hash, float *ms_dedup, float *ms_prune) {
     const int TB = 256;
@@ -240,6 +262,38 @@ static pcsf_status dedup_and_prune(pcsf_model *m, const WinSpace &ws, uint32_t n
         CK(cudaGetLastError());
     }
     if (m->timing) CK(cudaEventRecord(m->ev[2], st));
+    if (fp32) {
+        PruneF32Args fa{};
+        fa.ws = ws;
+        fa.uniq = m->uniq.as<uint32_t>();
+        fa.n_unique = d_nuniq_slot;
+        fa.program = m->d_program;
+        fa.n_ops = (int)m->host.program.size();
+        fa.n_gemm = (int)m->host.gemm_edges.size();
+        fa.max_stack = m->host.max_stack;
+        fa.stagger_ns = m->stagger_ns;
+        fa.nwarp = m->prune_f32_nwarp;
+        for (int w = 0; w < 2; ++w) {
+            fa.pstream[w] = m->d_pstream32[w];
+            fa.leafPT[w] = m->d_leafPT32[w];
+            fa.pi[w] = m->d_pi[w];
+            fa.logz[w] = m->logz.as<double>() + (size_t)w * nwin;
+        }
+        const uint32_t twf = (uint32_t)m->prune_f32_nwarp * 16;
+        const uint32_t mt = (nwin + twf - 1) / twf;
+        const unsigned gridf = std::min<uint32_t>((uint32_t)m->sm_count, std::max<uint32_t>(1u, mt));
+        m->launches++; k_prune_f32<<<gridf, (m->prune_f32_nwarp + 1) * 32, m->prune_f32_smem, st>>>(fa);
+        CK(cudaGetLastError());
+        if (m->timing) {
+            CK(cudaEventRecord(m->ev[3], st));
+            CK(cudaEventSynchronize(m->ev[3]));
+            float t;
+            CK(cudaEventElapsedTime(&t, m->ev[0], m->ev[1])); *ms_hash += t;
+            CK(cudaEventElapsedTime(&t, m->ev[1], m->ev[2])); *ms_dedup += t;
+            CK(cudaEventElapsedTime(&t, m->ev[2], m->ev[3])); *ms_prune += t;
+        }
+        return PCSF_OK;
+    }
     PruneArgs pa{};
     pa.ws = ws;
     pa.uniq = m->uniq.as<uint32_t>();
@@ -248,6 +302,8 @@ static pcsf_status dedup_and_prune(pcsf_model *m, const WinSpace &ws, uint32_t n
     pa.n_ops = (int)m->host.program.size();
     pa.n_gemm = (int)m->host.gemm_edges.size();
     pa.max_stack = m->host.max_stack;
+    pa.stagger_ns = m->stagger_ns;
+    pa.nwarp = m->prune_nwarp;
     for (int w = 0; w < 2; ++w) {
         pa.pstream[w] = m->d_pstream[w];
         pa.leafPT[w] = m->d_leafPT[w];
@@ -256,9 +312,10 @@ static pcsf_status dedup_and_prune(pcsf_model *m, const WinSpace &ws, uint32_t n
         pa.logz[w] = m->logz.as<double>() + (size_t)w * nwin;
         pa.anc[w] = want_anc ? m->anc.as<double>() + (size_t)w * nwin : nullptr;
     }
-    const uint32_t max_tiles = (nwin + PR_TILE_W - 1) / PR_TILE_W;
+    const uint32_t tile_w = (uint32_t)m->prune_nwarp * 8;
+    const uint32_t max_tiles = (nwin + tile_w - 1) / tile_w;
     const unsigned grid = std::min<uint32_t>((uint32_t)m->sm_count, std::max<uint32_t>(1u, max_tiles));
-    m->launches++; k_prune<false><<<grid, PR_THREADS, m->prune_smem, st>>>(pa);
+    m->launches++; k_prune<false><<<grid, (m->prune_nwarp + 1) * 32, m->prune_smem, st>>>(pa);
     CK(cudaGetLastError());
     if (m->timing) {
         CK(cudaEventRecord(m->ev[3], st));
@@ -299,7 +356,8 @@ extern "C" pcsf_status pcsf_tracks_device(pcsf_model *m, const uint8_t *d_seqs, 
     if (!m || L < 0 || ld < L || (L > 0 && !d_seqs)) return fail(PCSF_ERR_INVALID, "pcsf_tracks: bad argument");
     if ((flags & PCSF_TRACKS_SCORES) && L > 2 && (!d_plus || !d_minus)) return fail(PCSF_ERR_INVALID, "plus/minus required");
     if ((flags & PCSF_TRACKS_BLS) && L > 0 && !d_bls) return fail(PCSF_ERR_INVALID, "bls required");
-    if (flags & PCSF_TRACKS_FP32) return fail(PCSF_ERR_UNSUPPORTED, "the FP32-class tensor path is not built yet");
+    if ((flags & PCSF_TRACKS_FP32) && m->prune_f32_smem > 227 * 1024)
+        return fail(PCSF_ERR_UNSUPPORTED, "tree too deep for the FP32-class tensor path");
     CK(cudaSetDevice(m->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     m->last = pcsf_tracks_stats{};
@@ -328,7 +386,7 @@ extern "C" pcsf_status pcsf_tracks_device(pcsf_model *m, const uint8_t *d_seqs, 
             const int64_t c0 = c * m->chunk_cols, c1 = std::min(W, c0 + m->chunk_cols);
             const uint32_t nwin = (uint32_t)(2 * (c1 - c0));
             WinSpace ws{m->codes.as<uint8_t>(), m->codes_ld, m->host.nl, 0, c0, nullptr};
-            if ((rc = dedup_and_prune(m, ws, nwin, !(flags & PCSF_TRACKS_NO_DEDUP), false, m->d_nuniq + c, d_pattern_index,
+            if ((rc = dedup_and_prune(m, ws, nwin, !(flags & PCSF_TRACKS_NO_DEDUP), false, (flags & PCSF_TRACKS_FP32) != 0, m->d_nuniq + c, d_pattern_index,
                                       2 * c0, st, &m->last.ms_hash, &m->last.ms_dedup, &m->last.ms_prune)))
                 return rc;
             if (m->timing) CK(cudaEventRecord(m->ev[0], st));
@@ -451,7 +509,7 @@ extern "C" pcsf_status pcsf_score_msa(pcsf_model *m, pcsf_strategy strategy, int
         CK(m->perwin.reserve((size_t)std::max<int64_t>(nwin, 1) * 32));
         if (nwin > 0) {
             float t0 = 0, t1 = 0, t2 = 0;
-            if ((rc = dedup_and_prune(m, ws, (uint32_t)nwin, true, anc != nullptr, m->d_nuniq, nullptr, 0, st, &t0, &t1, &t2)))
+            if ((rc = dedup_and_prune(m, ws, (uint32_t)nwin, true, anc != nullptr, false, m->d_nuniq, nullptr, 0, st, &t0, &t1, &t2)))
                 return rc;
             k_scatter_list<<<(unsigned)((nwin + 255) / 256), 256, 0, st>>>(
                 (uint32_t)nwin, m->pidx.as<uint32_t>(), m->logz.as<double>(), m->logz.as<double>() + nwin,
@@ -476,7 +534,7 @@ extern "C" pcsf_status pcsf_score_msa(pcsf_model *m, pcsf_strategy strategy, int
         b.d_phylo = phylo ? d_phylo : nullptr;
         b.d_anc = anc ? d_anc : nullptr;
         if ((rc = mle_run(m->host, b, m->d_eig, m->d_bl, m->d_program, m->d_pi, m->d_logpi, m->mle, m->sm_count,
-                          m->prune_smem, st, g_err, &m->launches)))
+                          m->prune_smem, m->prune_nwarp, st, g_err, &m->launches)))
             return rc;
         // BLS for MLE uses the same per-alignment sum kernel with phylo/anc disabled
         if (bls) {

@@ -168,3 +168,46 @@ def test_build_tracks_golden(golden_dir):
     print(f"build-tracks golden: {flips} printed digits differ (FP64 path expects 0)")
     assert flips == 0
     dm.close()
+
+
+@pytest.mark.parametrize("name,L", [("12flies", 400), ("58mammals", 600), ("100vertebrates", 300), ("53birds", 500)])
+def test_fp32_tensor_path_within_contract(name, L):
+    """FP32-class tensor path (split-TF32 mma + per-window log-scaling): |delta| <= 1e-3 decibans (the contract);
+    asserted at 2e-4 against the oracle and against the FP64 path; BLS and pattern indices are unaffected."""
+    model = load_model(name)
+    seqs = random_alignment(model.nl, L, seed=77 + L, gap=0.35, conserve=0.8)
+    dm = capi.DeviceModel(model)
+    f64 = dm.tracks(seqs, want_patterns=True)
+    f32 = dm.tracks(seqs, want_patterns=True, fp32=True)
+    ref_p, ref_m, ref_b, _, _ = oracle_tracks(model, seqs)
+    d = max(np.abs(f32["plus"] - ref_p).max(), np.abs(f32["minus"] - ref_m).max())
+    print(f"{name}: FP32-class path max |delta| vs oracle = {d:.3e} decibans")
+    assert d <= 2e-4
+    assert max(np.abs(f32["plus"] - f64["plus"]).max(), np.abs(f32["minus"] - f64["minus"]).max()) <= 2e-4
+    assert np.array_equal(f32["bls"], ref_b) and np.array_equal(f32["pattern_index"], f64["pattern_index"])
+    dm.close()
+
+
+def test_fp32_path_extreme_columns_do_not_underflow():
+    """All-certain, maximally diverged columns: with 58 leaves the raw likelihood is ~1e-150 (far below FP32's
+    range, fine for FP64) -> the log-scaled FP32 path must still agree; with 100 leaves even the reference's
+    unscaled FP64 product underflows (z = 0 -> log 0 = -inf, fixed_lik.hpp:431) while the scaled path stays finite."""
+    rng = np.random.default_rng(5)
+    model = load_model("58mammals")
+    seqs = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, size=(model.nl, 300))]
+    dm = capi.DeviceModel(model)
+    f32 = dm.tracks(seqs, fp32=True)
+    ref_p, ref_m, _, _, _ = oracle_tracks(model, seqs)
+    assert np.isfinite(ref_p).all() and np.isfinite(ref_m).all()
+    assert max(np.abs(f32["plus"] - ref_p).max(), np.abs(f32["minus"] - ref_m).max()) <= 1e-3
+    dm.close()
+    model = load_model("100vertebrates")
+    seqs = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, size=(model.nl, 300))]
+    dm = capi.DeviceModel(model)
+    f32, f64 = dm.tracks(seqs, fp32=True), dm.tracks(seqs)
+    ref_p, ref_m, _, _, _ = oracle_tracks(model, seqs)
+    ref = np.concatenate([ref_p, ref_m])
+    assert (~np.isfinite(ref)).sum() > 0, "this input is meant to underflow the reference's FP64 product"
+    assert np.array_equal(np.isfinite(np.concatenate([f64["plus"], f64["minus"]])), np.isfinite(ref))
+    assert np.isfinite(f32["plus"]).all() and np.isfinite(f32["minus"]).all()
+    dm.close()

@@ -345,6 +345,7 @@ __host__ __device__ inline size_t prune_smem_bytes(int nl, int n_ops, int max_st
     size_t b = (size_t)PR_NSTAGE * PR_TILE_BYTES;            // P stages
     b += (size_t)nwarp * (max_stack > 0 ? max_stack : 1) * 4096;  // stacks
     b += (size_t)((nl * nwarp * 8 + 15) / 16) * 16;          // leaf codon ids
+    b += (size_t)nwarp * 8 * 8;                              // window offsets
     b += (size_t)((n_ops * 4 + 15) / 16) * 16;               // program
     b += 4 * 64 * 8;                                         // pi, logpi x 2 models
     b += 2 * PR_NSTAGE * 8;                                  // mbarriers
@@ -359,6 +360,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) k_prune(const PruneArgs a) {
     double *stage_buf = reinterpret_cast<double *>(sp_); sp_ += (size_t)PR_NSTAGE * PR_TILE_BYTES;
     double2 *stack = reinterpret_cast<double2 *>(sp_); sp_ += (size_t)PR_NWARP * (a.max_stack > 0 ? a.max_stack : 1) * 4096;
     uint8_t *ids = sp_; sp_ += (size_t)((a.ws.nl * PR_TILE_W + 15) / 16) * 16;
+    int64_t *s_woff = reinterpret_cast<int64_t *>(sp_); sp_ += (size_t)PR_TILE_W * 8;
     int32_t *prog = reinterpret_cast<int32_t *>(sp_); sp_ += (size_t)((a.n_ops * 4 + 15) / 16) * 16;
     double *s_pi = reinterpret_cast<double *>(sp_); sp_ += 4 * 64 * 8;   // [model][pi 64 | logpi 64]
     uint64_t *full = reinterpret_cast<uint64_t *>(sp_);
@@ -408,22 +410,29 @@ __global__ void __launch_bounds__(PR_THREADS, 1) k_prune(const PruneArgs a) {
         TileDesc td{};
         if (PER_TILE) td = a.tiles[tile];
         named_bar_sync(1, PR_NWARP * 32);
-        for (int i = tid; i < a.ws.nl * PR_TILE_W; i += PR_NWARP * 32) {
-            const int s = i / PR_TILE_W, wi = i % PR_TILE_W;
+        // window -> (column offset, strand) once per window, then species-major byte gathers with independent loads
+        if (tid < PR_TILE_W) {
             uint32_t lw;
             if (PER_TILE) {
-                lw = td.win0 + (uint32_t)(wi < td.count ? wi : td.count - 1);
+                lw = td.win0 + (uint32_t)(tid < td.count ? tid : td.count - 1);
             } else {
-                uint32_t u = tile * PR_TILE_W + wi;
+                uint32_t u = tile * PR_TILE_W + tid;
                 if (u >= n_unique) u = n_unique - 1;
                 lw = a.uniq[u];
             }
             int64_t o; uint32_t strand;
             if (a.ws.mode == 0) { o = a.ws.c0 + (lw >> 1); strand = lw & 1; }
             else { o = a.ws.win_off[lw]; strand = 0; }
-            const uint8_t *p = a.ws.codes + (int64_t)s * a.ws.ld + o;
+            s_woff[tid] = (o << 1) | strand;
+        }
+        named_bar_sync(1, PR_NWARP * 32);
+#pragma unroll 4
+        for (int i = tid; i < a.ws.nl * PR_TILE_W; i += PR_NWARP * 32) {
+            const int s = i / PR_TILE_W, wi = i - s * PR_TILE_W;
+            const int64_t ow = s_woff[wi];
+            const uint8_t *p = a.ws.codes + (int64_t)s * a.ws.ld + (ow >> 1);
             const uint32_t x0 = p[0], x1 = p[1], x2 = p[2];
-            ids[i] = (uint8_t)(strand ? codon_minus(x0, x1, x2) : codon_plus(x0, x1, x2));
+            ids[i] = (uint8_t)((ow & 1) ? codon_minus(x0, x1, x2) : codon_plus(x0, x1, x2));
         }
         named_bar_sync(1, PR_NWARP * 32);
         // Warps w and w+4 share an SMSP and would otherwise run the program in lockstep: both in the DMMA phase,

@@ -21,7 +21,7 @@ namespace pcsf {
 
 constexpr int PF_MAX_NWARP = 8;    // more warps do not help this kernel and would cap registers below its need
 constexpr int PF_THREADS = (PF_MAX_NWARP + 1) * 32;   // launch bound; the launch uses (nwarp + 1) * 32
-constexpr int PF_NSTAGE = 2;
+constexpr int PF_NSTAGE = 3;
 constexpr int PF_TILE_BYTES = 2 * NS * NS * 4;   // 32 KB: hi and lo of one 64x64 P
 constexpr int PF_STACK_ENTRY = 4096 + 256;       // 16 windows x 64 floats + per-thread exponent pair
 
@@ -43,6 +43,7 @@ __host__ __device__ inline size_t prune_f32_smem_bytes(int nl, int n_ops, int ma
     size_t b = (size_t)PF_NSTAGE * PF_TILE_BYTES;
     b += (size_t)nwarp * (max_stack > 0 ? max_stack : 1) * PF_STACK_ENTRY;
     b += (size_t)((nl * nwarp * 16 + 15) / 16) * 16;
+    b += (size_t)nwarp * 16 * 8;
     b += (size_t)((n_ops * 4 + 15) / 16) * 16;
     b += 2 * 64 * 8;
     b += 2 * PF_NSTAGE * 8;
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) k_prune_f32(const PruneF32Args 
     float *stage_buf = reinterpret_cast<float *>(sp_); sp_ += (size_t)PF_NSTAGE * PF_TILE_BYTES;
     unsigned char *stack = sp_; sp_ += (size_t)PF_NWARP * (a.max_stack > 0 ? a.max_stack : 1) * PF_STACK_ENTRY;
     uint8_t *ids = sp_; sp_ += (size_t)((a.ws.nl * PF_TILE_W + 15) / 16) * 16;
+    int64_t *s_woff = reinterpret_cast<int64_t *>(sp_); sp_ += (size_t)PF_TILE_W * 8;
     int32_t *prog = reinterpret_cast<int32_t *>(sp_); sp_ += (size_t)((a.n_ops * 4 + 15) / 16) * 16;
     double *s_pi = reinterpret_cast<double *>(sp_); sp_ += 2 * 64 * 8;
     uint64_t *full = reinterpret_cast<uint64_t *>(sp_);
@@ -106,17 +108,23 @@ __global__ void __launch_bounds__(PF_THREADS, 1) k_prune_f32(const PruneF32Args 
     uint32_t use = 0;
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         named_bar_sync(1, PF_NWARP * 32);
-        for (int i = tid; i < a.ws.nl * PF_TILE_W; i += PF_NWARP * 32) {
-            const int s = i / PF_TILE_W, wi = i % PF_TILE_W;
-            uint32_t u = tile * PF_TILE_W + wi;
+        if (tid < PF_TILE_W) {
+            uint32_t u = tile * PF_TILE_W + tid;
             if (u >= n_unique) u = n_unique - 1;
             const uint32_t lw = a.uniq[u];
             int64_t o; uint32_t strand;
             if (a.ws.mode == 0) { o = a.ws.c0 + (lw >> 1); strand = lw & 1; }
             else { o = a.ws.win_off[lw]; strand = 0; }
-            const uint8_t *p = a.ws.codes + (int64_t)s * a.ws.ld + o;
+            s_woff[tid] = (o << 1) | strand;
+        }
+        named_bar_sync(1, PF_NWARP * 32);
+#pragma unroll 4
+        for (int i = tid; i < a.ws.nl * PF_TILE_W; i += PF_NWARP * 32) {
+            const int s = i / PF_TILE_W, wi = i - s * PF_TILE_W;
+            const int64_t ow = s_woff[wi];
+            const uint8_t *p = a.ws.codes + (int64_t)s * a.ws.ld + (ow >> 1);
             const uint32_t x0 = p[0], x1 = p[1], x2 = p[2];
-            ids[i] = (uint8_t)(strand ? codon_minus(x0, x1, x2) : codon_plus(x0, x1, x2));
+            ids[i] = (uint8_t)((ow & 1) ? codon_minus(x0, x1, x2) : codon_plus(x0, x1, x2));
         }
         named_bar_sync(1, PF_NWARP * 32);
         if (warp >= PF_NWARP / 2 && a.stagger_ns) __nanosleep(a.stagger_ns);   // phase offset, see k_prune

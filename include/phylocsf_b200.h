@@ -78,7 +78,8 @@ int pcsf_abi_version(void);
 #define PCSF_TRACKS_SCORES   0x1u  /* plus[]/minus[] decibans */
 #define PCSF_TRACKS_BLS      0x2u  /* bls[] */
 #define PCSF_TRACKS_NO_DEDUP 0x4u  /* prune every window, do not deduplicate site patterns */
-#define PCSF_TRACKS_FP32     0x8u  /* FP32-class tensor path: split-TF32 MMA + per-window log-scaling (|delta| <= 1e-3 decibans) */
+#define PCSF_TRACKS_FP32     0x8u  /* FP32-class tensor path: split-TF32 mma.sync + per-window log-scaling (|delta| <= 1e-3 decibans) */
+#define PCSF_TRACKS_TC5      0x10u /* FP32-class path on tcgen05/TMEM (5th-gen tensor cores), same contract as FP32 */
 
 typedef struct {
     int64_t n_windows;        /* 2 * max(L-2, 0) */

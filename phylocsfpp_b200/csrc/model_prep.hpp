@@ -45,6 +45,8 @@ struct EcmHost {
     // FP32-class tensor path (split TF32): tiles of 2048 float4 {hi0, hi1, lo0, lo1}, HMMA.1688 fragment order
     std::vector<float> pstream32;
     std::vector<float> leafPT32;  // nl x 65 x 64 floats
+    // tcgen05 path: one 32 KB tile per edge in step order, UMMA K-major no-swizzle B layout, N = 128 = [hi | lo]
+    std::vector<float> pstream_tc5;
 };
 
 struct ModelHost {
@@ -56,6 +58,9 @@ struct ModelHost {
     std::vector<int32_t> program;
     std::vector<int> gemm_edges;  // node id of the g-th GEMM op
     int max_stack = 0;
+    // tcgen05 path: the same program with every edge (leaf edges too) as one GEMM step
+    std::vector<uint32_t> tc5_steps;   // arg | kind << 16 | post-op flags
+    std::vector<int> tc5_edges;        // node id of the edge of step s
     std::vector<BlsNode> bls_prog;
     int bls_depth = 0;
     double bls_all = 0.0;         // all_species_branch_length (additional_scores.hpp:56)
@@ -220,6 +225,24 @@ inline void to_fragment_order_tf32(const double *P, float *tile) {
             }
 }
 
+// ---- tcgen05 path ------------------------------------------------------------------------------------------
+// Step word: bits 0-15 leaf id (leaf steps), bits 16-17 kind, then post-op flags.
+enum : uint32_t { T5_LEAF_SET = 0, T5_LEAF_MUL = 1, T5_INNER = 2, T5_PUSH = 1u << 18, T5_POP_MUL = 1u << 19, T5_END = 1u << 20 };
+
+// One edge as the B operand of tcgen05.mma kind::tf32 (K-major, no swizzle): B[n][k], n = 0..127, k = 0..63 with
+// B[n][k] = hi(P[n][k]) for n < 64 and lo(P[n-64][k]) for n >= 64, so that D[w][0:64] + D[w][64:128] = sum_k A[w][k] P[.][k].
+// Chunk j (k = 8j..8j+7) is 4 KB contiguous; inside a chunk 8-row x 16-byte core matrices: 8-row group stride 256 B
+// (SBO), the two K halves 128 B apart (LBO).
+inline void to_tc5_tile(const double *P, float *tile /* 8192 floats */) {
+    for (int n = 0; n < 128; ++n)
+        for (int k = 0; k < NS; ++k) {
+            const double p = P[(n & 63) * NS + k];
+            const float hi = tf32_rna((float)p);
+            const float v = n < 64 ? hi : tf32_rna((float)(p - (double)hi));
+            tile[(k / 8) * 1024 + (n / 8) * 64 + ((k % 8) / 4) * 32 + (n % 8) * 4 + (k % 4)] = v;
+        }
+}
+
 inline void to_leaf_table(const double *P, double *pt /* 65 x 64 */) {
     for (int a = 0; a < NS; ++a) {
         double rs = 0.0;
@@ -335,6 +358,25 @@ inline std::string prepare_model(ModelHost &m, int nl, const int16_t *c1, const 
     detail::emit_partial(m, m.n - 1, need, sp);
     m.program.push_back(mk_op(OP_END, 0));
     if ((int)m.gemm_edges.size() != nl - 2) return "internal error: GEMM count";
+    // the same program as GEMM-only steps for the tcgen05 path
+    m.tc5_steps.clear(); m.tc5_edges.clear();
+    for (int32_t op : m.program) {
+        const int code = op >> 16, arg = op & 0xffff;
+        if (code == OP_GATHER_SET || code == OP_GATHER_MUL) {
+            m.tc5_steps.push_back((uint32_t)arg | ((code == OP_GATHER_SET ? T5_LEAF_SET : T5_LEAF_MUL) << 16));
+            m.tc5_edges.push_back(arg);
+        } else if (code == OP_GEMM) {
+            m.tc5_steps.push_back(T5_INNER << 16);
+            m.tc5_edges.push_back(m.gemm_edges[arg]);
+        } else if (code == OP_PUSH) {
+            m.tc5_steps.back() |= T5_PUSH;
+        } else if (code == OP_POP_MUL) {
+            m.tc5_steps.back() |= T5_POP_MUL;
+        } else if (code == OP_END) {
+            m.tc5_steps.back() |= T5_END;
+        }
+    }
+    if ((int)m.tc5_steps.size() != 2 * nl - 2) return "internal error: tcgen05 step count";
     // BLS program
     uint64_t lo, hi;
     m.bls_prog.clear();
@@ -365,6 +407,9 @@ inline std::string prepare_model(ModelHost &m, int nl, const int16_t *c1, const 
         e.pstream32.resize(m.gemm_edges.size() * (size_t)2 * NS * NS);
         for (size_t g = 0; g < m.gemm_edges.size(); ++g)
             to_fragment_order_tf32(e.P.data() + (size_t)m.gemm_edges[g] * NS * NS, e.pstream32.data() + g * 2 * NS * NS);
+        e.pstream_tc5.resize(m.tc5_edges.size() * (size_t)8192);
+        for (size_t st = 0; st < m.tc5_edges.size(); ++st)
+            to_tc5_tile(e.P.data() + (size_t)m.tc5_edges[st] * NS * NS, e.pstream_tc5.data() + st * 8192);
         e.leafPT32.resize(e.leafPT.size());
         for (size_t i = 0; i < e.leafPT.size(); ++i) e.leafPT32[i] = (float)e.leafPT[i];
     }

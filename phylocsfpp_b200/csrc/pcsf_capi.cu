@@ -18,6 +18,7 @@
 #include "kernels.cuh"
 #include "mle.cuh"
 #include "prune_f32.cuh"
+#include "prune_tc5.cuh"
 
 using namespace pcsf;
 
@@ -57,6 +58,10 @@ struct pcsf_model {
     float *d_pstream32[2] = {nullptr, nullptr}, *d_leafPT32[2] = {nullptr, nullptr};
     size_t prune_f32_smem = 0;
     int prune_f32_nwarp = 8;
+    float *d_pstream_tc5[2] = {nullptr, nullptr};
+    uint32_t *d_tc5_steps = nullptr;
+    float *d_tc5_scratch = nullptr;      // stack spill of k_prune_tc5: [sm_count][2][max_stack][T5_STACK_ENTRY_FLOATS]
+    size_t prune_tc5_smem = 0;
     int32_t *d_program = nullptr;
     BlsNode *d_bls_prog = nullptr;
     float *d_bl = nullptr;
@@ -124,6 +129,7 @@ extern "C" pcsf_status pcsf_model_create(const pcsf_model_desc *d, int device, p
         if ((st = upload(e.leafPT.data(), e.leafPT.size() * 8, (void **)&m->d_leafPT[w]))) return st;
         if ((st = upload(e.pstream32.data(), e.pstream32.size() * 4, (void **)&m->d_pstream32[w]))) return st;
         if ((st = upload(e.leafPT32.data(), e.leafPT32.size() * 4, (void **)&m->d_leafPT32[w]))) return st;
+        if ((st = upload(e.pstream_tc5.data(), e.pstream_tc5.size() * 4, (void **)&m->d_pstream_tc5[w]))) return st;
         if ((st = upload(e.pi, 64 * 8, (void **)&m->d_pi[w]))) return st;
         if ((st = upload(e.logpi, 64 * 8, (void **)&m->d_logpi[w]))) return st;
         std::vector<double> eig(64 + 2 * 4096);
@@ -133,6 +139,10 @@ extern "C" pcsf_status pcsf_model_create(const pcsf_model_desc *d, int device, p
         if ((st = upload(eig.data(), eig.size() * 8, (void **)&m->d_eig[w]))) return st;
     }
     if ((st = upload(m->host.program.data(), m->host.program.size() * 4, (void **)&m->d_program))) return st;
+    if ((st = upload(m->host.tc5_steps.data(), m->host.tc5_steps.size() * 4, (void **)&m->d_tc5_steps))) return st;
+    CK(cudaMalloc(&m->d_tc5_scratch, (size_t)m->sm_count * 2 * std::max(1, m->host.max_stack) * T5_STACK_ENTRY_FLOATS * 4));
+    m->prune_tc5_smem = prune_tc5_smem_bytes(m->host.nl, (int)m->host.tc5_steps.size());
+    CK(cudaFuncSetAttribute(k_prune_tc5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->prune_tc5_smem));
     if ((st = upload(m->host.bls_prog.data(), m->host.bls_prog.size() * sizeof(BlsNode), (void **)&m->d_bls_prog))) return st;
     if ((st = upload(m->host.bl.data(), m->host.bl.size() * 4, (void **)&m->d_bl))) return st;
     {
@@ -173,11 +183,11 @@ extern "C" void pcsf_model_destroy(pcsf_model *m) {
     if (!m) return;
     cudaSetDevice(m->device);
     for (int w = 0; w < 2; ++w) {
-        cudaFree(m->d_pstream[w]); cudaFree(m->d_leafPT[w]); cudaFree(m->d_pstream32[w]); cudaFree(m->d_leafPT32[w]); cudaFree(m->d_pi[w]); cudaFree(m->d_logpi[w]);
+        cudaFree(m->d_pstream[w]); cudaFree(m->d_leafPT[w]); cudaFree(m->d_pstream32[w]); cudaFree(m->d_leafPT32[w]); cudaFree(m->d_pstream_tc5[w]); cudaFree(m->d_pi[w]); cudaFree(m->d_logpi[w]);
         cudaFree(m->d_eig[w]);
     }
     cudaFree(m->d_program); cudaFree(m->d_bls_prog); cudaFree(m->d_bl); cudaFree(m->d_gemm_edges);
-    cudaFree(m->d_bad); cudaFree(m->d_nuniq);
+    cudaFree(m->d_bad); cudaFree(m->d_nuniq); cudaFree(m->d_tc5_steps); cudaFree(m->d_tc5_scratch);
     DevBuf *bufs[] = {&m->codes, &m->klo, &m->khi, &m->slot, &m->flag, &m->uniq, &m->pidx, &m->table, &m->slotmin,
                       &m->bsums, &m->logz, &m->anc, &m->misc, &m->io_in, &m->io_out, &m->perwin, &m->mle};
     for (DevBuf *b : bufs) b->release();
@@ -216,7 +226,7 @@ static inline uint32_t next_pow2(uint64_t x) {
 
 // dedup + prune for one window space of `nwin` local windows; results land in m->pidx (pattern id per
 // window), m->logz / m->anc (per pattern); *d_nuniq_slot receives the pattern count.
-static pcsf_status dedup_and_prune(pcsf_model *m, const WinSpace &ws, uint32_t nwin, bool dedup, bool want_anc, bool fp32,
+static pcsf_status dedup_and_prune(pcsf_model *m, const WinSpace &ws, uint32_t nwin, bool dedup, bool want_anc, int prec /* 0 FP64 DMMA, 1 split-TF32 mma.sync, 2 tcgen05 */,
                                    uint32_t *d_nuniq_slot, uint32_t *d_pattern_out, int64_t out_base,
                                    cudaStream_t st, float *ms_hash, float *ms_dedup, float *ms_prune) {
     const int TB = 256;
@@ -262,7 +272,35 @@ static pcsf_status dedup_and_prune(pcsf_model *m, const WinSpace &ws, uint32_t n
         CK(cudaGetLastError());
     }
     if (m->timing) CK(cudaEventRecord(m->ev[2], st));
-    if (fp32) {
+    if (prec == 2) {
+        PruneTc5Args ta{};
+        ta.ws = ws;
+        ta.uniq = m->uniq.as<uint32_t>();
+        ta.n_unique = d_nuniq_slot;
+        ta.steps = m->d_tc5_steps;
+        ta.n_steps = (int)m->host.tc5_steps.size();
+        ta.max_stack = m->host.max_stack;
+        ta.scratch = m->d_tc5_scratch;
+        for (int w = 0; w < 2; ++w) {
+            ta.pstream[w] = m->d_pstream_tc5[w];
+            ta.pi[w] = m->d_pi[w];
+            ta.logz[w] = m->logz.as<double>() + (size_t)w * nwin;
+        }
+        const uint32_t mp = (nwin + 255) / 256;
+        const unsigned gridt = std::min<uint32_t>((uint32_t)m->sm_count, std::max<uint32_t>(1u, mp));
+        m->launches++; k_prune_tc5<<<gridt, T5_THREADS, m->prune_tc5_smem, st>>>(ta);
+        CK(cudaGetLastError());
+        if (m->timing) {
+            CK(cudaEventRecord(m->ev[3], st));
+            CK(cudaEventSynchronize(m->ev[3]));
+            float t;
+            CK(cudaEventElapsedTime(&t, m->ev[0], m->ev[1])); *ms_hash += t;
+            CK(cudaEventElapsedTime(&t, m->ev[1], m->ev[2])); *ms_dedup += t;
+            CK(cudaEventElapsedTime(&t, m->ev[2], m->ev[3])); *ms_prune += t;
+        }
+        return PCSF_OK;
+    }
+    if (prec == 1) {
         PruneF32Args fa{};
         fa.ws = ws;
         fa.uniq = m->uniq.as<uint32_t>();
@@ -386,7 +424,7 @@ extern "C" pcsf_status pcsf_tracks_device(pcsf_model *m, const uint8_t *d_seqs, 
             const int64_t c0 = c * m->chunk_cols, c1 = std::min(W, c0 + m->chunk_cols);
             const uint32_t nwin = (uint32_t)(2 * (c1 - c0));
             WinSpace ws{m->codes.as<uint8_t>(), m->codes_ld, m->host.nl, 0, c0, nullptr};
-            if ((rc = dedup_and_prune(m, ws, nwin, !(flags & PCSF_TRACKS_NO_DEDUP), false, (flags & PCSF_TRACKS_FP32) != 0, m->d_nuniq + c, d_pattern_index,
+            if ((rc = dedup_and_prune(m, ws, nwin, !(flags & PCSF_TRACKS_NO_DEDUP), false, (flags & PCSF_TRACKS_TC5) ? 2 : (flags & PCSF_TRACKS_FP32) ? 1 : 0, m->d_nuniq + c, d_pattern_index,
                                       2 * c0, st, &m->last.ms_hash, &m->last.ms_dedup, &m->last.ms_prune)))
                 return rc;
             if (m->timing) CK(cudaEventRecord(m->ev[0], st));
@@ -509,7 +547,7 @@ extern "C" pcsf_status pcsf_score_msa(pcsf_model *m, pcsf_strategy strategy, int
         CK(m->perwin.reserve((size_t)std::max<int64_t>(nwin, 1) * 32));
         if (nwin > 0) {
             float t0 = 0, t1 = 0, t2 = 0;
-            if ((rc = dedup_and_prune(m, ws, (uint32_t)nwin, true, anc != nullptr, false, m->d_nuniq, nullptr, 0, st, &t0, &t1, &t2)))
+            if ((rc = dedup_and_prune(m, ws, (uint32_t)nwin, true, anc != nullptr, 0, m->d_nuniq, nullptr, 0, st, &t0, &t1, &t2)))
                 return rc;
             k_scatter_list<<<(unsigned)((nwin + 255) / 256), 256, 0, st>>>(
                 (uint32_t)nwin, m->pidx.as<uint32_t>(), m->logz.as<double>(), m->logz.as<double>() + nwin,

@@ -211,3 +211,47 @@ def test_fp32_path_extreme_columns_do_not_underflow():
     assert np.array_equal(np.isfinite(np.concatenate([f64["plus"], f64["minus"]])), np.isfinite(ref))
     assert np.isfinite(f32["plus"]).all() and np.isfinite(f32["minus"]).all()
     dm.close()
+
+
+@pytest.mark.parametrize("name,L", [("12flies", 400), ("58mammals", 700), ("100vertebrates", 300), ("53birds", 500), ("7yeast", 130)])
+def test_tcgen05_path_within_contract(name, L):
+    """tcgen05/TMEM path (kind::tf32 MMA with hi/lo split operands, leaf gathers as one-hot GEMMs, per-window
+    log-scaling): |delta| <= 1e-3 decibans is the contract; asserted at 2e-4 against the oracle and the FP64 path."""
+    model = load_model(name)
+    seqs = random_alignment(model.nl, L, seed=177 + L, gap=0.35, conserve=0.8)
+    dm = capi.DeviceModel(model)
+    f64 = dm.tracks(seqs, want_patterns=True)
+    t5 = dm.tracks(seqs, want_patterns=True, tc5=True)
+    ref_p, ref_m, ref_b, _, _ = oracle_tracks(model, seqs)
+    d = max(np.abs(t5["plus"] - ref_p).max(), np.abs(t5["minus"] - ref_m).max())
+    print(f"{name}: tcgen05 path max |delta| vs oracle = {d:.3e} decibans")
+    assert d <= 2e-4
+    assert max(np.abs(t5["plus"] - f64["plus"]).max(), np.abs(t5["minus"] - f64["minus"]).max()) <= 2e-4
+    assert np.array_equal(t5["bls"], ref_b) and np.array_equal(t5["pattern_index"], f64["pattern_index"])
+    dm.close()
+
+
+def test_tcgen05_path_many_tiles_and_no_dedup():
+    """More window pairs than SMs (persistent loop, ring wrap-around, both phases of every barrier) and the
+    no-dedup route; compared with the FP64 path on the same input."""
+    model = load_model("29mammals")
+    seqs = random_alignment(model.nl, 60000, seed=4242, gap=0.3, conserve=0.7)
+    dm = capi.DeviceModel(model)
+    f64 = dm.tracks(seqs, bls=False)
+    t5 = dm.tracks(seqs, bls=False, tc5=True)
+    t5n = dm.tracks(seqs, bls=False, tc5=True, dedup=False)
+    d = max(np.abs(t5["plus"] - f64["plus"]).max(), np.abs(t5["minus"] - f64["minus"]).max())
+    assert d <= 2e-4, d
+    assert np.array_equal(t5["plus"], t5n["plus"]) and np.array_equal(t5["minus"], t5n["minus"])
+    dm.close()
+
+
+def test_tcgen05_path_extreme_columns_do_not_underflow():
+    rng = np.random.default_rng(6)
+    model = load_model("100vertebrates")
+    seqs = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, size=(model.nl, 300))]
+    dm = capi.DeviceModel(model)
+    t5, f32 = dm.tracks(seqs, tc5=True), dm.tracks(seqs, fp32=True)
+    assert np.isfinite(t5["plus"]).all() and np.isfinite(t5["minus"]).all()
+    assert max(np.abs(t5["plus"] - f32["plus"]).max(), np.abs(t5["minus"] - f32["minus"]).max()) <= 1e-3
+    dm.close()

@@ -122,7 +122,9 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="columns of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dedup", action="store_true")
-    ap.add_argument("--precision", default="f64", choices=["f64", "f32"], help="f64: FP64 DMMA path (parity anchor); f32: split-TF32 tensor path")
+    ap.add_argument("--precision", default="tc5", choices=["f64", "f32", "tc5"],
+                    help="tc5: tcgen05/TMEM split-TF32 path (fastest path inside the 1e-3 deciban contract); "
+                         "f64: FP64 DMMA path (parity anchor, byte-identical wig text); f32: split-TF32 mma.sync path")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -187,7 +189,7 @@ def main():
     minus = torch.empty(Wn, dtype=torch.float64, device=dev)
     bls = torch.empty(B, dtype=torch.float64, device=dev)
     flags = (capi.TRACKS_SCORES | capi.TRACKS_BLS | (capi.TRACKS_NO_DEDUP if args.no_dedup else 0)
-             | (capi.TRACKS_FP32 if args.precision == "f32" else 0))
+             | {"f64": 0, "f32": capi.TRACKS_FP32, "tc5": capi.TRACKS_TC5}[args.precision])
     stream = torch.cuda.current_stream()
 
     def step():
@@ -253,6 +255,20 @@ def main():
     tstats = dm.tracks_device_finish(stream.cuda_stream)
     dm.set_timing(False)
 
+    # one instrumented step of the other precisions, for the side-by-side the north star asks for
+    other = {}
+    if rank == 0:
+        base = flags & ~(capi.TRACKS_FP32 | capi.TRACKS_TC5)
+        dm.set_timing(True)
+        for pname, pflag in (("f64", 0), ("f32", capi.TRACKS_FP32), ("tc5", capi.TRACKS_TC5)):
+            if pname == args.precision:
+                continue
+            dm.tracks_device(seqs.data_ptr(), B, ld, base | pflag, plus.data_ptr(), minus.data_ptr(), bls.data_ptr(), 0, stream.cuda_stream)
+            o = dm.tracks_device_finish(stream.cuda_stream)
+            other[pname] = {"ms_prune_per_step": o["ms_prune"],
+                            "columns_per_s_kernels_only": B / (1e-3 * sum(o[k] for k in ("ms_pack", "ms_hash", "ms_dedup", "ms_prune", "ms_scatter", "ms_bls")))}
+        dm.set_timing(False)
+
     if rank == 0:
         F = flops_per_pruning(nl)
         n_prune_launch = max(1, tstats["n_chunks"])
@@ -264,17 +280,34 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "profiles", "peaks_fp64.json")))
         except Exception:
             pass
-        peak = peaks.get("micro", {}).get("dmma_tflops", 37.16)
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_prune_traffic.json"))).get("dram_bytes_per_launch")
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_prune_traffic.json"))).get(
+                {"f64": "dram_bytes_per_launch", "f32": "dram_bytes_per_launch_f32", "tc5": "dram_bytes_per_launch_tc5"}[args.precision])
         except Exception:
             pass
+        if args.precision == "f64":
+            kernel, dtype = "k_prune", "f64"
+            peak = peaks.get("micro", {}).get("dmma_tflops", 37.16)
+            peak_source = ("FP64 DMMA (mma.sync.m8n8k4.f64) register-loop peak measured on this pool "
+                           "(profiles/peaks_fp64.json); MEASURED_PEAKS.json carries no FP64 figure")
+            executed = achieved
+        else:
+            # executed tensor flops per pruning: every edge is a (window x 64 x 64) product; the split operands make it
+            # 3 TF32 products (mma.sync path; leaves are gathers there) or 4 for inner + 2 for leaf edges (tcgen05 path)
+            kernel, dtype = ("k_prune_f32", "tf32x3/f32") if args.precision == "f32" else ("k_prune_tc5", "tf32x2x2/f32")
+            peak = peaks.get("tf32_tflops", 764.2)
+            peak_source = ("dense TF32 tensor peak = cuBLAS TF32 GEMM 8192^3 measured on this pool (profiles/peaks_fp64.json; "
+                           "MEASURED_PEAKS.json carries bf16 only: 1605 TFLOP/s burst, TF32 is half rate); `achieved` counts "
+                           "ALGORITHMIC flops (one FP product per term), `executed_tflops` what the tensor pipe ran")
+            mult = (3.0 * 8192 * (nl - 2)) / F if args.precision == "f32" else (4.0 * 8192 * (nl - 2) + 2.0 * 8192 * nl) / F
+            executed = achieved * mult
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "dtype": dtype, "data": "synthetic",
             "config": {"workload": workload, "model": args.model, "leaves": nl, "columns_per_step_per_gpu": B,
+                       "precision": args.precision,
                        "missing_fraction": 0.30, "l2_policy": "inputs larger than L2 (%.0f MB per step)" % (nl * B / 1e6),
                        "dedup": not args.no_dedup, "unique_pattern_ratio": tstats["n_unique"] / max(1, tstats["n_windows"]),
                        "sharding": "independent column batches per rank, no collective"},
@@ -282,14 +315,14 @@ def main():
                     "steps": n_e2e, "api": "pcsf_tracks (C-ABI, pinned host buffers)"},
             "gpu_launches": stats["n_launches"] * args.steps,
             "clocks": clocks,
-            "roofline": {"kernel": "k_prune", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": "FP64 DMMA (mma.sync.m8n8k4.f64) register-loop peak measured on this pool "
-                                        "(profiles/peaks_fp64.json); MEASURED_PEAKS.json carries no FP64 figure",
+            "roofline": {"kernel": kernel, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": traffic, "executed_tflops": executed,
+                         "executed_frac": executed / peak, "peak_source": peak_source,
                          "flop_per_launch": flop_per_launch, "ms_per_launch": ms_per_launch,
                          "prunings_per_launch": tstats["n_unique"] * 2 / n_prune_launch},
             "stages_ms": {k: tstats[k] for k in ("ms_pack", "ms_hash", "ms_dedup", "ms_prune", "ms_scatter", "ms_bls")},
             "checksum": checksum,
+            "other_precisions": other,
         }
         if world == 1 and not args.no_cpu_baseline:
             S = args.cpu_sample or 3000 * ncores

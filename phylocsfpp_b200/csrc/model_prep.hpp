@@ -45,8 +45,10 @@ struct EcmHost {
     // FP32-class tensor path (split TF32): tiles of 2048 float4 {hi0, hi1, lo0, lo1}, HMMA.1688 fragment order
     std::vector<float> pstream32;
     std::vector<float> leafPT32;  // nl x 65 x 64 floats
-    // tcgen05 path: one 32 KB tile per edge in step order, UMMA K-major no-swizzle B layout, N = 128 = [hi | lo]
+    // tcgen05 path: one 32 KB tile per inner edge in step order (UMMA K-major no-swizzle B layout, N = 128 = [hi | lo])
+    // and one 17 KB shared-memory gather table per leaf in program order (64 rows x 68 floats)
     std::vector<float> pstream_tc5;
+    std::vector<float> leaf_tc5;
 };
 
 struct ModelHost {
@@ -58,9 +60,11 @@ struct ModelHost {
     std::vector<int32_t> program;
     std::vector<int> gemm_edges;  // node id of the g-th GEMM op
     int max_stack = 0;
-    // tcgen05 path: the same program with every edge (leaf edges too) as one GEMM step
-    std::vector<uint32_t> tc5_steps;   // arg | kind << 16 | post-op flags
+    // tcgen05 path: the same program as one step per inner edge (GEMM) + what follows it up to the next GEMM
+    std::vector<uint32_t> tc5_steps;   // leaf1 | leaf2 << 8 | post-op << 16 | END << 20
     std::vector<int> tc5_edges;        // node id of the edge of step s
+    std::vector<int> tc5_leaf_order;   // leaves in the order the program gathers them
+    int tc5_first[2] = {0, 0};         // the cherry the program starts with
     std::vector<BlsNode> bls_prog;
     int bls_depth = 0;
     double bls_all = 0.0;         // all_species_branch_length (additional_scores.hpp:56)
@@ -226,10 +230,12 @@ inline void to_fragment_order_tf32(const double *P, float *tile) {
 }
 
 // ---- tcgen05 path ------------------------------------------------------------------------------------------
-// Step word: bits 0-15 leaf id (leaf steps), bits 16-17 kind, then post-op flags.
-enum : uint32_t { T5_LEAF_SET = 0, T5_LEAF_MUL = 1, T5_INNER = 2, T5_PUSH = 1u << 18, T5_POP_MUL = 1u << 19, T5_END = 1u << 20 };
+// Step word: bits 0-7 leaf1, 8-15 leaf2, 16-17 post-op (what the program does between this GEMM and the next), bit 20 END.
+enum : uint32_t { T5_NONE = 0, T5_MUL_LEAF = 1, T5_PUSH_CHERRY = 2, T5_POP_MUL = 3, T5_END = 1u << 20 };
+constexpr int T5_LEAF_ROW = 68;                      // floats per gather-table row: 272 B stride spreads the rows over the banks
+constexpr int T5_LEAF_FLOATS = 64 * T5_LEAF_ROW;     // 17408 B per leaf
 
-// One edge as the B operand of tcgen05.mma kind::tf32 (K-major, no swizzle): B[n][k], n = 0..127, k = 0..63 with
+// One inner edge as the B operand of tcgen05.mma kind::tf32 (K-major, no swizzle): B[n][k], n = 0..127, k = 0..63 with
 // B[n][k] = hi(P[n][k]) for n < 64 and lo(P[n-64][k]) for n >= 64, so that D[w][0:64] + D[w][64:128] = sum_k A[w][k] P[.][k].
 // Chunk j (k = 8j..8j+7) is 4 KB contiguous; inside a chunk 8-row x 16-byte core matrices: 8-row group stride 256 B
 // (SBO), the two K halves 128 B apart (LBO).
@@ -241,6 +247,14 @@ inline void to_tc5_tile(const double *P, float *tile /* 8192 floats */) {
             const float v = n < 64 ? hi : tf32_rna((float)(p - (double)hi));
             tile[(k / 8) * 1024 + (n / 8) * 64 + ((k % 8) / 4) * 32 + (n % 8) * 4 + (k % 4)] = v;
         }
+}
+// Leaf gather table: row x (a certain codon) = P_l[:, x] in FP32.  A gap/N codon (id 64) is the all-ones message on
+// this path: the row sums of P_l are 1 to FP32 precision (instance.hpp:625-639 normalises the rows).
+inline void to_tc5_leaf(const double *P, float *tab /* T5_LEAF_FLOATS */) {
+    for (int x = 0; x < NS; ++x) {
+        for (int a = 0; a < NS; ++a) tab[x * T5_LEAF_ROW + a] = (float)P[a * NS + x];
+        for (int a = NS; a < T5_LEAF_ROW; ++a) tab[x * T5_LEAF_ROW + a] = 0.f;
+    }
 }
 
 inline void to_leaf_table(const double *P, double *pt /* 65 x 64 */) {
@@ -358,25 +372,41 @@ inline std::string prepare_model(ModelHost &m, int nl, const int16_t *c1, const 
     detail::emit_partial(m, m.n - 1, need, sp);
     m.program.push_back(mk_op(OP_END, 0));
     if ((int)m.gemm_edges.size() != nl - 2) return "internal error: GEMM count";
-    // the same program as GEMM-only steps for the tcgen05 path
-    m.tc5_steps.clear(); m.tc5_edges.clear();
-    for (int32_t op : m.program) {
-        const int code = op >> 16, arg = op & 0xffff;
-        if (code == OP_GATHER_SET || code == OP_GATHER_MUL) {
-            m.tc5_steps.push_back((uint32_t)arg | ((code == OP_GATHER_SET ? T5_LEAF_SET : T5_LEAF_MUL) << 16));
-            m.tc5_edges.push_back(arg);
-        } else if (code == OP_GEMM) {
-            m.tc5_steps.push_back(T5_INNER << 16);
-            m.tc5_edges.push_back(m.gemm_edges[arg]);
-        } else if (code == OP_PUSH) {
-            m.tc5_steps.back() |= T5_PUSH;
-        } else if (code == OP_POP_MUL) {
-            m.tc5_steps.back() |= T5_POP_MUL;
-        } else if (code == OP_END) {
-            m.tc5_steps.back() |= T5_END;
+    // the same program as one step per GEMM for the tcgen05 path; between two GEMMs the program is one of
+    //   (nothing) | GATHER_MUL l | PUSH GATHER_SET l1 GATHER_MUL l2 | POP_MUL        (see emit_partial)
+    m.tc5_steps.clear(); m.tc5_edges.clear(); m.tc5_leaf_order.clear();
+    {
+        const std::vector<int32_t> &pr = m.program;
+        auto code = [&](size_t i) { return i < pr.size() ? (int)(pr[i] >> 16) : -1; };
+        auto arg = [&](size_t i) { return (int)(pr[i] & 0xffff); };
+        if (code(0) != OP_GATHER_SET || code(1) != OP_GATHER_MUL) return "internal error: program does not start with a cherry";
+        m.tc5_first[0] = arg(0); m.tc5_first[1] = arg(1);
+        m.tc5_leaf_order.push_back(arg(0)); m.tc5_leaf_order.push_back(arg(1));
+        size_t i = 2;
+        while (code(i) == OP_GEMM) {
+            uint32_t w = 0;
+            m.tc5_edges.push_back(m.gemm_edges[arg(i)]);
+            ++i;
+            if (code(i) == OP_GATHER_MUL) {
+                w = (uint32_t)arg(i) | (T5_MUL_LEAF << 16);
+                m.tc5_leaf_order.push_back(arg(i));
+                ++i;
+            } else if (code(i) == OP_PUSH) {
+                if (code(i + 1) != OP_GATHER_SET || code(i + 2) != OP_GATHER_MUL) return "internal error: PUSH not followed by a cherry";
+                w = (uint32_t)arg(i + 1) | ((uint32_t)arg(i + 2) << 8) | (T5_PUSH_CHERRY << 16);
+                m.tc5_leaf_order.push_back(arg(i + 1)); m.tc5_leaf_order.push_back(arg(i + 2));
+                i += 3;
+            } else if (code(i) == OP_POP_MUL) {
+                w = T5_POP_MUL << 16;
+                ++i;
+            }
+            if (code(i) == OP_END) { w |= T5_END; ++i; }
+            m.tc5_steps.push_back(w);
         }
+        if (m.tc5_steps.empty() && code(i) == OP_END) ++i;      // two leaves: the cherry is the whole tree
+        if (i != pr.size() || (int)m.tc5_steps.size() != nl - 2 || (int)m.tc5_leaf_order.size() != nl)
+            return "internal error: tcgen05 step list";
     }
-    if ((int)m.tc5_steps.size() != 2 * nl - 2) return "internal error: tcgen05 step count";
     // BLS program
     uint64_t lo, hi;
     m.bls_prog.clear();
@@ -410,6 +440,9 @@ inline std::string prepare_model(ModelHost &m, int nl, const int16_t *c1, const 
         e.pstream_tc5.resize(m.tc5_edges.size() * (size_t)8192);
         for (size_t st = 0; st < m.tc5_edges.size(); ++st)
             to_tc5_tile(e.P.data() + (size_t)m.tc5_edges[st] * NS * NS, e.pstream_tc5.data() + st * 8192);
+        e.leaf_tc5.resize(m.tc5_leaf_order.size() * (size_t)T5_LEAF_FLOATS);
+        for (size_t k = 0; k < m.tc5_leaf_order.size(); ++k)
+            to_tc5_leaf(e.P.data() + (size_t)m.tc5_leaf_order[k] * NS * NS, e.leaf_tc5.data() + k * T5_LEAF_FLOATS);
         e.leafPT32.resize(e.leafPT.size());
         for (size_t i = 0; i < e.leafPT.size(); ++i) e.leafPT32[i] = (float)e.leafPT[i];
     }

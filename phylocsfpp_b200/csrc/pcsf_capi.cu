@@ -58,7 +58,7 @@ struct pcsf_model {
     float *d_pstream32[2] = {nullptr, nullptr}, *d_leafPT32[2] = {nullptr, nullptr};
     size_t prune_f32_smem = 0;
     int prune_f32_nwarp = 8;
-    float *d_pstream_tc5[2] = {nullptr, nullptr};
+    float *d_pstream_tc5[2] = {nullptr, nullptr}, *d_leaf_tc5[2] = {nullptr, nullptr};
     uint32_t *d_tc5_steps = nullptr;
     float *d_tc5_scratch = nullptr;      // stack spill of k_prune_tc5: [sm_count][2][max_stack][T5_STACK_ENTRY_FLOATS]
     size_t prune_tc5_smem = 0;
@@ -130,6 +130,7 @@ extern "C" pcsf_status pcsf_model_create(const pcsf_model_desc *d, int device, p
         if ((st = upload(e.pstream32.data(), e.pstream32.size() * 4, (void **)&m->d_pstream32[w]))) return st;
         if ((st = upload(e.leafPT32.data(), e.leafPT32.size() * 4, (void **)&m->d_leafPT32[w]))) return st;
         if ((st = upload(e.pstream_tc5.data(), e.pstream_tc5.size() * 4, (void **)&m->d_pstream_tc5[w]))) return st;
+        if ((st = upload(e.leaf_tc5.data(), e.leaf_tc5.size() * 4, (void **)&m->d_leaf_tc5[w]))) return st;
         if ((st = upload(e.pi, 64 * 8, (void **)&m->d_pi[w]))) return st;
         if ((st = upload(e.logpi, 64 * 8, (void **)&m->d_logpi[w]))) return st;
         std::vector<double> eig(64 + 2 * 4096);
@@ -183,7 +184,7 @@ extern "C" void pcsf_model_destroy(pcsf_model *m) {
     if (!m) return;
     cudaSetDevice(m->device);
     for (int w = 0; w < 2; ++w) {
-        cudaFree(m->d_pstream[w]); cudaFree(m->d_leafPT[w]); cudaFree(m->d_pstream32[w]); cudaFree(m->d_leafPT32[w]); cudaFree(m->d_pstream_tc5[w]); cudaFree(m->d_pi[w]); cudaFree(m->d_logpi[w]);
+        cudaFree(m->d_pstream[w]); cudaFree(m->d_leafPT[w]); cudaFree(m->d_pstream32[w]); cudaFree(m->d_leafPT32[w]); cudaFree(m->d_pstream_tc5[w]); cudaFree(m->d_leaf_tc5[w]); cudaFree(m->d_pi[w]); cudaFree(m->d_logpi[w]);
         cudaFree(m->d_eig[w]);
     }
     cudaFree(m->d_program); cudaFree(m->d_bls_prog); cudaFree(m->d_bl); cudaFree(m->d_gemm_edges);
@@ -280,9 +281,12 @@ static pcsf_status dedup_and_prune(pcsf_model *m, const WinSpace &ws, uint32_t n
         ta.steps = m->d_tc5_steps;
         ta.n_steps = (int)m->host.tc5_steps.size();
         ta.max_stack = m->host.max_stack;
+        ta.first0 = m->host.tc5_first[0];
+        ta.first1 = m->host.tc5_first[1];
         ta.scratch = m->d_tc5_scratch;
         for (int w = 0; w < 2; ++w) {
             ta.pstream[w] = m->d_pstream_tc5[w];
+            ta.leaftab[w] = m->d_leaf_tc5[w];
             ta.pi[w] = m->d_pi[w];
             ta.logz[w] = m->logz.as<double>() + (size_t)w * nwin;
         }

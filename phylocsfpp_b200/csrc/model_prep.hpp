@@ -65,6 +65,7 @@ struct ModelHost {
     std::vector<int> tc5_edges;        // node id of the edge of step s
     std::vector<int> tc5_leaf_order;   // leaves in the order the program gathers them
     int tc5_first[2] = {0, 0};         // the cherry the program starts with
+    int tc5_smem_depth = 0;            // stack depth with the most pushes (kept in shared memory by k_prune_tc5)
     std::vector<BlsNode> bls_prog;
     int bls_depth = 0;
     double bls_all = 0.0;         // all_species_branch_length (additional_scores.hpp:56)
@@ -404,6 +405,16 @@ inline std::string prepare_model(ModelHost &m, int nl, const int16_t *c1, const 
             m.tc5_steps.push_back(w);
         }
         if (m.tc5_steps.empty() && code(i) == OP_END) ++i;      // two leaves: the cherry is the whole tree
+        {
+            int depth = 0, cnt[16] = {0};
+            for (uint32_t w : m.tc5_steps) {
+                const uint32_t post = (w >> 16) & 3u;
+                if (post == T5_PUSH_CHERRY) { if (depth < 16) cnt[depth]++; ++depth; }
+                else if (post == T5_POP_MUL) --depth;
+            }
+            m.tc5_smem_depth = 0;
+            for (int d = 1; d < 16; ++d) if (cnt[d] > cnt[m.tc5_smem_depth]) m.tc5_smem_depth = d;
+        }
         if (i != pr.size() || (int)m.tc5_steps.size() != nl - 2 || (int)m.tc5_leaf_order.size() != nl)
             return "internal error: tcgen05 step list";
     }

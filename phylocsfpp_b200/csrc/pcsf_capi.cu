@@ -62,6 +62,7 @@ struct pcsf_model {
     uint32_t *d_tc5_steps = nullptr;
     float *d_tc5_scratch = nullptr;      // stack spill of k_prune_tc5: [sm_count][2][max_stack][T5_STACK_ENTRY_FLOATS]
     size_t prune_tc5_smem = 0;
+    int tc5_nstage = 2, tc5_nlstage = 3;
     int32_t *d_program = nullptr;
     BlsNode *d_bls_prog = nullptr;
     float *d_bl = nullptr;
@@ -142,7 +143,10 @@ extern "C" pcsf_status pcsf_model_create(const pcsf_model_desc *d, int device, p
     if ((st = upload(m->host.program.data(), m->host.program.size() * 4, (void **)&m->d_program))) return st;
     if ((st = upload(m->host.tc5_steps.data(), m->host.tc5_steps.size() * 4, (void **)&m->d_tc5_steps))) return st;
     CK(cudaMalloc(&m->d_tc5_scratch, (size_t)m->sm_count * 2 * std::max(1, m->host.max_stack) * T5_STACK_ENTRY_FLOATS * 4));
-    m->prune_tc5_smem = prune_tc5_smem_bytes(m->host.nl, (int)m->host.tc5_steps.size());
+    prune_tc5_pick_stages(m->host.nl, (int)m->host.tc5_steps.size(), &m->tc5_nstage, &m->tc5_nlstage);
+    if (const char *e = getenv("PCSF_TC5_NSTAGE")) m->tc5_nstage = std::max(2, std::min(m->tc5_nstage, atoi(e)));
+    if (const char *e = getenv("PCSF_TC5_NLSTAGE")) m->tc5_nlstage = std::max(3, std::min(m->tc5_nlstage, atoi(e)));
+    m->prune_tc5_smem = prune_tc5_smem_bytes(m->host.nl, (int)m->host.tc5_steps.size(), m->tc5_nstage, m->tc5_nlstage);
     CK(cudaFuncSetAttribute(k_prune_tc5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->prune_tc5_smem));
     if ((st = upload(m->host.bls_prog.data(), m->host.bls_prog.size() * sizeof(BlsNode), (void **)&m->d_bls_prog))) return st;
     if ((st = upload(m->host.bl.data(), m->host.bl.size() * 4, (void **)&m->d_bl))) return st;
@@ -283,6 +287,8 @@ static pcsf_status dedup_and_prune(pcsf_model *m, const WinSpace &ws, uint32_t n
         ta.max_stack = m->host.max_stack;
         ta.first0 = m->host.tc5_first[0];
         ta.first1 = m->host.tc5_first[1];
+        ta.nstage = m->tc5_nstage;
+        ta.nlstage = m->tc5_nlstage;
         ta.scratch = m->d_tc5_scratch;
         for (int w = 0; w < 2; ++w) {
             ta.pstream[w] = m->d_pstream_tc5[w];

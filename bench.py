@@ -293,14 +293,14 @@ def main():
                            "(profiles/peaks_fp64.json); MEASURED_PEAKS.json carries no FP64 figure")
             executed = achieved
         else:
-            # executed tensor flops per pruning: every edge is a (window x 64 x 64) product; the split operands make it
-            # 3 TF32 products (mma.sync path; leaves are gathers there) or 4 for inner + 2 for leaf edges (tcgen05 path)
-            kernel, dtype = ("k_prune_f32", "tf32x3/f32") if args.precision == "f32" else ("k_prune_tc5", "tf32x2x2/f32")
+            # executed tensor flops per pruning: every inner edge is a (window x 64 x 64) product done as 3 TF32 products
+            # (hi*hi, hi*lo, lo*hi) on either tensor path; leaf edges are gathers (no tensor work) on both
+            kernel, dtype = ("k_prune_f32", "tf32x3/f32") if args.precision == "f32" else ("k_prune_tc5", "tf32x3/f32")
             peak = peaks.get("tf32_tflops", 764.2)
             peak_source = ("dense TF32 tensor peak = cuBLAS TF32 GEMM 8192^3 measured on this pool (profiles/peaks_fp64.json; "
                            "MEASURED_PEAKS.json carries bf16 only: 1605 TFLOP/s burst, TF32 is half rate); `achieved` counts "
                            "ALGORITHMIC flops (one FP product per term), `executed_tflops` what the tensor pipe ran")
-            mult = (3.0 * 8192 * (nl - 2)) / F if args.precision == "f32" else (4.0 * 8192 * (nl - 2) + 2.0 * 8192 * nl) / F
+            mult = (3.0 * 8192 * (nl - 2)) / F
             executed = achieved * mult
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -1,0 +1,320 @@
+// maf.hpp — MAF alignment reader with the reference's block-concatenation semantics.
+//
+// Mirrors parallel_maf_reader::get_next_alignment (reference src/parallel_file_reader.hpp:430-700):
+//   * `s` lines: `s <species>.<chrom> <start0> <size> <strand> <srcSize> <text>` (space separated, :180-245);
+//     species = text before the first '.', lower-cased (:489-507); species unknown to the model are skipped with a
+//     one-time warning (:509-524); `i`/`e`/`q` lines are ignored (:597-600);
+//   * the first matched row of a chain's first block is the reference: start_pos = start0 + 1 (:528-554);
+//   * build-tracks (concatenate): the next block is appended iff same chrom and start0 == (start_pos-1) + cumulative
+//     reference length (:494-505); absent species are padded with 'N' (:603-611); a chain that crosses a multiple of
+//     BREAKPOINT_POS keeps reading until >= 2 more reference bases are in, is truncated to exactly +2 and the cursor is
+//     rewound to the first block after the crossing block (:456-473, :547-569, :616-629, :671-679);
+//   * columns where the reference row has '-' are deleted from every row (:631-669);
+//   * score-msa (no concatenation): one block = one alignment, any reference strand.
+// Parallelism differs from the reference on purpose: instead of page-aligned byte ranges whose owners re-read a
+// neighbour's block (:254-357, :396-425), a parallel pre-scan records per block what the chain logic needs (the `s` lines up
+// to the first matched species), a serial pass over that metadata cuts the chains exactly as a single reader would,
+// and worker threads parse whole chains.  The output is that of the reference with jobs = 1 for any thread count.
+#pragma once
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <mutex>
+#include <thread>
+
+#include "model.hpp"
+
+namespace host {
+
+constexpr int64_t BREAKPOINT_POS = 1000000;
+
+struct SLine {
+    const char *ident = nullptr; int ident_len = 0;       // species.chrom
+    int64_t start0 = 0, size = 0, src_size = 0;
+    char strand = '+';
+    const char *seq = nullptr; size_t seq_len = 0;
+};
+
+// strtok_r(" ") semantics on one line [p, e): runs of spaces collapse.  Numbers via atoi (32 bit, as the reference).
+inline bool parse_s_line(const char *p, const char *e, SLine &s) {
+    const char *tok[7]; int len[7]; int n = 0;
+    while (p < e && n < 7) {
+        while (p < e && *p == ' ') ++p;
+        if (p >= e) break;
+        const char *q = p;
+        while (q < e && *q != ' ') ++q;
+        tok[n] = p; len[n] = (int)(q - p); ++n;
+        p = q;
+    }
+    if (n < 7) return false;
+    auto num = [](const char *t, int l) {
+        int64_t v = 0;
+        int i = 0;
+        const bool neg = l > 0 && t[0] == '-';
+        if (neg) i = 1;
+        for (; i < l && t[i] >= '0' && t[i] <= '9'; ++i) v = v * 10 + (t[i] - '0');
+        return (int64_t)(int32_t)(neg ? -v : v);      // atoi
+    };
+    s.ident = tok[1]; s.ident_len = len[1];
+    s.start0 = num(tok[2], len[2]); s.size = num(tok[3], len[3]);
+    s.strand = tok[4][0];
+    s.src_size = num(tok[5], len[5]);
+    s.seq = tok[6]; s.seq_len = (size_t)len[6];
+    while (s.seq_len && (s.seq[s.seq_len - 1] == '\r')) --s.seq_len;
+    return true;
+}
+
+struct Alignment {            // alignment_t (parallel_file_reader.hpp:19-44) with seqs as one [nl][L] matrix
+    int64_t start_pos = 0, chrom_len = 0;
+    char strand = '+';
+    std::string chrom;
+    int64_t L = 0;
+    std::vector<uint8_t> seqs;   // [nl][L]
+};
+
+class MafFile {
+public:
+    struct PreLine { int64_t start0; const char *chrom; int chrom_len; };
+    struct BlockMeta {
+        size_t off = 0, end = 0;
+        std::vector<PreLine> pre;        // unmatched `s` lines before the first matched one
+        bool has_ref = false;
+        uint16_t ref_id = 0;
+        int64_t start0 = 0, size = 0, src_size = 0;
+        char strand = '+';
+        const char *chrom = nullptr; int chrom_len = 0;
+        const char *species = nullptr; int species_len = 0;
+    };
+    struct Chain {
+        std::vector<size_t> blocks;
+        int64_t start_pos = 0, chrom_len = 0, keep_cols = -1;     // keep_cols >= 0: truncate to that many reference bases
+        char strand = '+';
+        std::string chrom;
+        int ref_id = -1;
+    };
+
+    MafFile(const std::string &path, const Model &model, bool concatenate, int threads) : model_(model), concatenate_(concatenate) {
+        fd_ = open(path.c_str(), O_RDONLY);
+        if (fd_ < 0) die("Cannot open %s", path.c_str());
+        size_ = (size_t)lseek(fd_, 0, SEEK_END);
+        if (size_ == 0) { mem_ = nullptr; return; }
+        mem_ = (const char *)mmap(nullptr, size_, PROT_READ, MAP_SHARED, fd_, 0);
+        if (mem_ == MAP_FAILED) die("Cannot map %s", path.c_str());
+        scan_blocks(std::max(1, threads));
+        build_chains();
+    }
+    ~MafFile() {
+        if (mem_ && size_) munmap((void *)mem_, size_);
+        if (fd_ >= 0) close(fd_);
+    }
+    size_t file_size() const { return size_; }
+    const std::vector<Chain> &chains() const { return chains_; }
+    size_t chain_bytes(const Chain &c) const { size_t b = 0; for (size_t i : c.blocks) b += blocks_[i].end - blocks_[i].off; return b; }
+    std::vector<std::string> unresolved() const { return std::vector<std::string>(unresolved_.begin(), unresolved_.end()); }
+
+    // Full parse of one chain (thread safe).  species_seen: [nl] flags, may be null.
+    void read_chain(const Chain &c, Alignment &aln, std::vector<uint8_t> *species_seen) const {
+        const int nl = model_.nl();
+        aln.start_pos = c.start_pos; aln.chrom_len = c.chrom_len; aln.strand = c.strand; aln.chrom = c.chrom;
+        aln.L = 0; aln.seqs.clear();
+        if (c.ref_id < 0) return;
+        std::vector<std::string> rows(nl);
+        std::string key;
+        for (size_t bi : c.blocks) {
+            const BlockMeta &b = blocks_[bi];
+            const char *p = mem_ + b.off, *end = mem_ + b.end;
+            while (p < end) {
+                const char *nlp = (const char *)memchr(p, '\n', (size_t)(end - p));
+                const char *le = nlp ? nlp : end;
+                if (*p == 's') {
+                    SLine s;
+                    if (parse_s_line(p, le, s)) {
+                        const char *dot = (const char *)memchr(s.ident, '.', (size_t)s.ident_len);
+                        const int sl = dot ? (int)(dot - s.ident) : s.ident_len;
+                        key.assign(s.ident, (size_t)sl);
+                        for (char &ch : key) ch = (char)tolower((unsigned char)ch);
+                        auto it = model_.seqid_to_phyloid.find(key);
+                        if (it != model_.seqid_to_phyloid.end()) {
+                            rows[it->second].append(s.seq, s.seq_len);
+                            if (species_seen) (*species_seen)[it->second] = 1;
+                        }
+                    }
+                }
+                p = le + 1;
+            }
+            const size_t new_len = rows[c.ref_id].size();                // absent species get N (:603-611)
+            for (int i = 0; i < nl; ++i)
+                if (rows[i].size() != new_len) {
+                    if (rows[i].size() > new_len) die("alignment rows of different length in block at byte %zu", b.off);
+                    rows[i].append(new_len - rows[i].size(), 'N');
+                }
+        }
+        // delete the columns where the reference has '-' (:631-669), then cut at the breakpoint + 2
+        const std::string &ref = rows[c.ref_id];
+        std::vector<uint32_t> keep;
+        keep.reserve(ref.size());
+        for (size_t i = 0; i < ref.size(); ++i) if (ref[i] != '-') keep.push_back((uint32_t)i);
+        size_t L = keep.size();
+        if (c.keep_cols >= 0 && (size_t)c.keep_cols < L) L = (size_t)c.keep_cols;
+        aln.L = (int64_t)L;
+        aln.seqs.resize((size_t)nl * L);
+        for (int s = 0; s < nl; ++s) {
+            const char *src = rows[s].data();
+            uint8_t *dst = aln.seqs.data() + (size_t)s * L;
+            for (size_t i = 0; i < L; ++i) dst[i] = (uint8_t)src[keep[i]];
+        }
+    }
+
+private:
+    void scan_range(size_t from, size_t to, std::vector<BlockMeta> &out, std::set<std::string> &unres) const {
+        // blocks whose "a " line starts in [from, to)
+        size_t pos = from;
+        auto at_block = [&](size_t p) { return p + 1 < size_ && mem_[p] == 'a' && mem_[p + 1] == ' ' && (p == 0 || mem_[p - 1] == '\n'); };
+        auto next_block = [&](size_t p) -> size_t {          // first block start >= p
+            while (p < size_) {
+                if (at_block(p)) return p;
+                const char *q = (const char *)memchr(mem_ + p, '\n', size_ - p);
+                if (!q) return size_;
+                p = (size_t)(q - mem_) + 1;
+            }
+            return size_;
+        };
+        if (from > 0) {   // align to a line start
+            const char *q = (const char *)memchr(mem_ + from - 1, '\n', size_ - from + 1);
+            pos = q ? (size_t)(q - mem_) + 1 : size_;
+        }
+        pos = next_block(pos);
+        std::string key;
+        while (pos < to && pos < size_) {
+            BlockMeta b;
+            b.off = pos;
+            const char *q = (const char *)memchr(mem_ + pos, '\n', size_ - pos);
+            size_t p = q ? (size_t)(q - mem_) + 1 : size_;
+            while (p < size_ && !at_block(p)) {
+                const char *nlp = (const char *)memchr(mem_ + p, '\n', size_ - p);
+                const size_t le = nlp ? (size_t)(nlp - mem_) : size_;
+                if (mem_[p] == 's' && !b.has_ref) {
+                    SLine s;
+                    if (parse_s_line(mem_ + p, mem_ + le, s)) {
+                        const char *dot = (const char *)memchr(s.ident, '.', (size_t)s.ident_len);
+                        if (!dot) die("expect format species_name.chrom_name in alignment file (byte %zu)", p);
+                        const int sl = (int)(dot - s.ident);
+                        key.assign(s.ident, (size_t)sl);
+                        for (char &ch : key) ch = (char)tolower((unsigned char)ch);
+                        auto it = model_.seqid_to_phyloid.find(key);
+                        if (it == model_.seqid_to_phyloid.end()) {
+                            b.pre.push_back(PreLine{s.start0, dot + 1, s.ident_len - sl - 1});
+                            unres.insert(key);
+                        } else {
+                            b.has_ref = true; b.ref_id = it->second;
+                            b.start0 = s.start0; b.size = s.size; b.src_size = s.src_size; b.strand = s.strand;
+                            b.chrom = dot + 1; b.chrom_len = s.ident_len - sl - 1;
+                            b.species = s.ident; b.species_len = sl;
+                        }
+                    }
+                } else if (mem_[p] == 's') {
+                    // later rows only matter for the unknown-species warning
+                    const char *sp = mem_ + p + 1;
+                    while (sp < mem_ + le && *sp == ' ') ++sp;
+                    const char *dot = (const char *)memchr(sp, '.', (size_t)(mem_ + le - sp));
+                    const char *spc = (const char *)memchr(sp, ' ', (size_t)(mem_ + le - sp));
+                    if (dot && (!spc || dot < spc)) {
+                        key.assign(sp, (size_t)(dot - sp));
+                        for (char &ch : key) ch = (char)tolower((unsigned char)ch);
+                        if (!model_.seqid_to_phyloid.count(key)) unres.insert(key);
+                    }
+                }
+                p = le + 1;
+            }
+            b.end = std::min(p, size_);
+            out.push_back(std::move(b));
+            pos = p;
+        }
+    }
+
+    void scan_blocks(int threads) {
+        std::vector<std::vector<BlockMeta>> parts(threads);
+        std::vector<std::set<std::string>> unres(threads);
+        std::vector<std::thread> th;
+        const size_t step = (size_ + threads - 1) / threads;
+        for (int t = 0; t < threads; ++t)
+            th.emplace_back([&, t] { scan_range(std::min(size_, t * step), std::min(size_, (t + 1) * step), parts[t], unres[t]); });
+        for (auto &x : th) x.join();
+        for (int t = 0; t < threads; ++t) {
+            for (auto &b : parts[t]) blocks_.push_back(std::move(b));
+            unresolved_.insert(unres[t].begin(), unres[t].end());
+        }
+    }
+
+    // get_next_alignment's control flow on the block metadata
+    void build_chains() {
+        const size_t nb = blocks_.size();
+        size_t pos = 0;
+        while (pos < nb) {
+            Chain c;
+            bool first_block = true, abort_next = !concatenate_, reached_bp = false, stop_saving = false;
+            size_t saved_pos = pos;
+            int64_t prev_cum = 0, cum_after_bp = 0;
+            while ((!abort_next || first_block) && pos < nb) {
+                if (!stop_saving) { if (reached_bp) stop_saving = true; saved_pos = pos; }
+                const size_t bi = pos++;
+                const BlockMeta &b = blocks_[bi];
+                if (reached_bp && prev_cum >= cum_after_bp + 2) abort_next = true;
+                if (!abort_next || first_block) {
+                    bool aborted = false;
+                    auto contiguous = [&](int64_t start0, const char *chrom, int chrom_len) {
+                        return (c.start_pos - 1) + prev_cum == start0 && (size_t)chrom_len == c.chrom.size() && memcmp(chrom, c.chrom.data(), c.chrom.size()) == 0;
+                    };
+                    if (!first_block) {
+                        for (const PreLine &pl : b.pre)
+                            if (!contiguous(pl.start0, pl.chrom, pl.chrom_len)) { aborted = true; break; }
+                        if (!aborted && b.has_ref && !contiguous(b.start0, b.chrom, b.chrom_len)) aborted = true;
+                    }
+                    if (aborted) {
+                        abort_next = true;
+                    } else if (b.has_ref) {
+                        const std::string who = std::string(b.species, (size_t)b.species_len) + "." + std::string(b.chrom, (size_t)b.chrom_len);
+                        if (c.ref_id == -1 && first_block) {
+                            c.start_pos = b.start0 + 1; c.chrom.assign(b.chrom, (size_t)b.chrom_len); c.chrom_len = b.src_size; c.strand = b.strand;
+                            c.ref_id = b.ref_id;
+                            prev_cum = b.size;
+                            if (b.strand != '+' && concatenate_) die("Reference sequence is not on the + strand (%s at position %ld)!", who.c_str(), (long)b.start0);
+                            const int64_t prev_end = c.start_pos, new_end = c.start_pos + b.size;
+                            if (!reached_bp && prev_end / BREAKPOINT_POS < new_end / BREAKPOINT_POS) { reached_bp = true; cum_after_bp = prev_cum; }
+                        } else if (!first_block) {
+                            const int64_t prev_end = c.start_pos + prev_cum, new_end = c.start_pos + prev_cum + b.size;
+                            prev_cum += b.size;
+                            if (!reached_bp && prev_end / BREAKPOINT_POS < new_end / BREAKPOINT_POS) { reached_bp = true; cum_after_bp = prev_cum; }
+                            if (c.ref_id != (int)b.ref_id)
+                                die("Encountered an alignment block that didn't start with the reference species: %s at position %ld!", who.c_str(), (long)b.start0);
+                            if (b.strand != '+' && concatenate_) die("Reference sequence is not on the + strand (%s at position %ld)!", who.c_str(), (long)b.start0);
+                        }
+                        c.blocks.push_back(bi);
+                    } else if (!first_block || true) {
+                        // a block without any species of the model contributes nothing
+                        if (c.ref_id >= 0 || first_block) c.blocks.push_back(bi);
+                    }
+                }
+                first_block = false;
+            }
+            if (reached_bp && prev_cum >= cum_after_bp + 2) abort_next = true;
+            if (abort_next && concatenate_) pos = saved_pos;
+            if (reached_bp && prev_cum > cum_after_bp + 2) c.keep_cols = cum_after_bp + 2;
+            chains_.push_back(std::move(c));
+        }
+    }
+
+    const Model &model_;
+    bool concatenate_;
+    int fd_ = -1;
+    size_t size_ = 0;
+    const char *mem_ = nullptr;
+    std::vector<BlockMeta> blocks_;
+    std::vector<Chain> chains_;
+    std::set<std::string> unresolved_;
+};
+
+}  // namespace host

@@ -1,0 +1,368 @@
+// phylocsf_b200 — reference-compatible command line host over libphylocsf_b200.so (include/phylocsf_b200.h).
+//
+//   phylocsf_b200 build-tracks [OPTIONS] <model> <alignments>...    (reference src/phylocsf++build_tracks.hpp:367-507)
+//   phylocsf_b200 score-msa    [OPTIONS] <model> <alignments>...    (reference src/phylocsf++score_msa.hpp:245-385)
+//
+// The host keeps what the reference keeps on the CPU: option handling (options before positionals,
+// src/arg_parse.hpp:111-115; BOOL = 1/true/one, :303), model loading, MAF reading, wig / scores text.  The likelihood
+// core is the CUDA library; there is no CPU fallback.  Worker threads parse whole alignment chains, call the C-ABI on
+// their GPU (thread t -> GPU t mod --gpus) and format the text; a writer appends the results in file order, so the
+// output does not depend on the thread or GPU count (the reference merges its per-job files in job order,
+// build_tracks.hpp:27-53,245-259).
+// Not in this tool: --output-phylo / --output-regions (PhyloCSF-HMM smoothing), the OMEGA and FIXED_MEAN strategies.
+#include <cinttypes>
+#include <chrono>
+#include <condition_variable>
+#include <cmath>
+
+#include "maf.hpp"
+
+using namespace host;
+
+namespace {
+
+struct Args {
+    std::map<std::string, std::string> opt;
+    std::vector<std::string> pos;
+    bool has(const std::string &k) const { return opt.count(k) > 0; }
+    std::string str(const std::string &k, const std::string &dflt = "") const { auto it = opt.find(k); return it == opt.end() ? dflt : it->second; }
+    bool boolean(const std::string &k, bool dflt) const {        // arg_parse.hpp:303
+        auto it = opt.find(k);
+        if (it == opt.end()) return dflt;
+        const std::string v = lower(it->second);
+        return v == "1" || v == "true" || v == "one";
+    }
+    int integer(const std::string &k, int dflt) const { auto it = opt.find(k); return it == opt.end() ? dflt : atoi(it->second.c_str()); }
+};
+
+Args parse_args(int argc, char **argv, const std::set<std::string> &known) {
+    Args a;
+    int i = 2;
+    for (; i < argc; ++i) {
+        const std::string t = argv[i];
+        if (t.rfind("--", 0) != 0) break;
+        const std::string k = t.substr(2);
+        if (!known.count(k)) die("Unknown option '%s'", t.c_str());
+        if (i + 1 >= argc) die("Option '%s' needs a value", t.c_str());
+        a.opt[k] = argv[++i];
+    }
+    for (; i < argc; ++i) {
+        if (strncmp(argv[i], "--", 2) == 0) die("Options have to be specified before the positional arguments ('%s')", argv[i]);
+        a.pos.push_back(argv[i]);
+    }
+    return a;
+}
+
+uint32_t precision_flag(const Args &a) {
+    const std::string p = lower(a.str("precision", "f64"));
+    if (p == "f64") return 0;
+    if (p == "tc5") return PCSF_TRACKS_TC5;
+    if (p == "f32") return PCSF_TRACKS_FP32;
+    die("--precision must be f64, tc5 or f32");
+}
+
+int64_t mod3(int64_t x) { x %= 3; return x < 0 ? x + 3 : x; }
+
+// In-order hand-over of per-chain text from the workers to the writer.
+struct OrderedSink {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<std::vector<std::string>> slots;      // [chain][stream]
+    std::vector<uint8_t> ready;
+    void resize(size_t n) { slots.assign(n, {}); ready.assign(n, 0); }
+    void put(size_t i, std::vector<std::string> &&v) {
+        { std::lock_guard<std::mutex> g(mu); slots[i] = std::move(v); ready[i] = 1; }
+        cv.notify_all();
+    }
+    std::vector<std::string> take(size_t i) {
+        std::unique_lock<std::mutex> g(mu);
+        cv.wait(g, [&] { return ready[i] != 0; });
+        return std::move(slots[i]);
+    }
+};
+
+void warn_unresolved(const MafFile &maf) {
+    for (const std::string &s : maf.unresolved())
+        printf("\033[33mWARNING: Not able to match species %s in alignment file to model (Use `--mapping` to fix it)!\033[0m\n", s.c_str());
+}
+
+// ------------------------------------------------------------------------------------------- build-tracks
+int main_build_tracks(int argc, char **argv) {
+    const Args a = parse_args(argc, argv, {"output-raw-phylo", "output-phylo", "output-regions", "power-threshold", "genome-length", "coding-exons",
+                                           "threads", "output", "mapping", "species", "gpus", "precision"});
+    if (a.pos.size() < 2) die("usage: phylocsf_b200 build-tracks [OPTIONS] <model> <alignments>...");
+    if (a.boolean("output-phylo", false) || a.boolean("output-regions", false))
+        die("--output-phylo / --output-regions (PhyloCSF-HMM smoothing) are not part of this tool");
+    const bool raw = a.boolean("output-raw-phylo", true);
+    // the reference reads --power-threshold with get_bool (build_tracks.hpp:416-417): anything but 1/true/one gives 0
+    const float threshold = a.has("power-threshold") ? (a.boolean("power-threshold", false) ? 1.0f : 0.0f) : 0.1f;
+    const int threads = std::max(1, a.integer("threads", (int)std::thread::hardware_concurrency()));
+    const int gpus = std::max(1, a.integer("gpus", 1));
+    const uint32_t pflag = precision_flag(a);
+
+    Model model;
+    load_model(model, a.pos[0], a.str("species"), a.str("mapping"));
+    const int nl = model.nl();
+    std::vector<pcsf_model *> dev(threads);
+    for (int t = 0; t < threads; ++t) dev[t] = create_device_model(model, t % gpus);
+    std::vector<std::vector<uint8_t>> seen(threads, std::vector<uint8_t>(nl, 0));
+    static const char *kFrames[6] = {"+1", "+2", "+3", "-1", "-2", "-3"};
+    int64_t total_cols = 0;
+    double t_gpu = 0.0;
+    const auto t_start = std::chrono::steady_clock::now();
+
+    for (size_t fi = 1; fi < a.pos.size(); ++fi) {
+        const std::string &path = a.pos[fi];
+        std::string out_dir = a.str("output");
+        if (out_dir.empty()) {
+            const size_t p = path.find_last_of('/');
+            out_dir = p == std::string::npos ? "./" : path.substr(0, p);
+        } else {
+            create_directory(out_dir);
+        }
+        MafFile maf(path, model, true, threads);
+        warn_unresolved(maf);
+        const std::vector<MafFile::Chain> &chains = maf.chains();
+        FILE *files[7];
+        const char *mode = fi > 1 ? "a" : "w";
+        files[0] = fopen((out_dir + "/PhyloCSFpower.wig").c_str(), mode);
+        for (int k = 0; k < 6; ++k) files[1 + k] = raw ? fopen((out_dir + "/PhyloCSFRaw" + kFrames[k] + ".wig").c_str(), mode) : nullptr;
+        if (!files[0] || (raw && !files[1])) die("Error creating output files in '%s'!", out_dir.c_str());
+
+        OrderedSink sink;
+        sink.resize(chains.size());
+        std::atomic<size_t> next{0};
+        std::atomic<int64_t> cols{0};
+        std::mutex gpu_time_mu;
+        std::vector<std::thread> workers;
+        for (int t = 0; t < threads; ++t)
+            workers.emplace_back([&, t] {
+                Alignment aln;
+                std::vector<double> plus, minus, bls;
+                double my_gpu = 0.0;
+                for (size_t ci = next++; ci < chains.size(); ci = next++) {
+                    std::vector<std::string> text(7);
+                    maf.read_chain(chains[ci], aln, &seen[t]);
+                    const int64_t L = aln.L;
+                    if (L > 0) {
+                        plus.resize((size_t)std::max<int64_t>(L - 2, 0)); minus.resize(plus.size()); bls.resize((size_t)L);
+                        const auto g0 = std::chrono::steady_clock::now();
+                        const pcsf_status st = pcsf_tracks(dev[t], aln.seqs.data(), L, L, PCSF_TRACKS_BLS | (raw ? PCSF_TRACKS_SCORES : 0) | pflag,
+                                                           plus.data(), minus.data(), bls.data(), nullptr, nullptr);
+                        my_gpu += std::chrono::duration<double>(std::chrono::steady_clock::now() - g0).count();
+                        if (st == PCSF_ERR_BAD_CHAR) { fprintf(stderr, "%s\n", pcsf_last_error()); exit(37); }      // translation.hpp:46-51
+                        if (st != PCSF_OK) die("pcsf_tracks: %s", pcsf_last_error());
+                        cols += L;
+                        char hdr[512];
+                        // power track (build_tracks.hpp:139-158)
+                        {
+                            std::string &o = text[0];
+                            const int64_t skip = mod3(3 - aln.start_pos);
+                            if (skip + 2 < L) {
+                                snprintf(hdr, sizeof hdr, "fixedStep chrom=%s start=%" PRId64 " step=3 span=3\n", aln.chrom.c_str(), aln.start_pos + skip);
+                                o += hdr;
+                            }
+                            for (int64_t pos = skip; pos + 2 < L; pos += 3) my_format(o, 4, (float)((bls[pos] + bls[pos + 1] + bls[pos + 2]) / 3.0));
+                        }
+                        // six raw tracks (build_tracks.hpp:160-216; frame arithmetic of update_seqs, parallel_file_reader.hpp:61-113)
+                        if (raw) {
+                            const float thr3 = threshold * 3;
+                            for (int k = 0; k < 6; ++k) {
+                                const bool fwd = k < 3;
+                                const int64_t frame = k % 3 + 1;
+                                int64_t o0, K;
+                                if (fwd) {
+                                    const int64_t skip = std::min<int64_t>(mod3(frame - aln.start_pos), L);
+                                    o0 = skip; K = (L - skip) / 3;
+                                } else {
+                                    const int64_t skip_r = std::min<int64_t>(mod3(frame - (aln.chrom_len - (aln.start_pos + L) + 2)), L);
+                                    o0 = (L - skip_r) % 3; K = (L - skip_r) / 3;
+                                }
+                                const std::vector<double> &src = fwd ? plus : minus;
+                                std::string &o = text[1 + k];
+                                int64_t prev = -4;
+                                for (int64_t xx = 0; xx < K; ++xx) {
+                                    const int64_t off = o0 + 3 * xx;
+                                    const float bsum = (float)(bls[off] + bls[off + 1] + bls[off + 2]);
+                                    if (bsum < thr3) continue;
+                                    const int64_t np = aln.start_pos + off;
+                                    if (prev + 3 != np) {
+                                        snprintf(hdr, sizeof hdr, "fixedStep chrom=%s start=%" PRId64 " step=3 span=3\n", aln.chrom.c_str(), np);
+                                        o += hdr;
+                                    }
+                                    prev = np;
+                                    my_format(o, 3, (float)src[off]);
+                                }
+                            }
+                        }
+                    }
+                    sink.put(ci, std::move(text));
+                }
+                std::lock_guard<std::mutex> g(gpu_time_mu);
+                t_gpu += my_gpu;
+            });
+        size_t bytes_done = 0;
+        for (size_t ci = 0; ci < chains.size(); ++ci) {
+            std::vector<std::string> text = sink.take(ci);
+            for (int k = 0; k < 7; ++k) if (files[k] && !text[k].empty()) fwrite(text[k].data(), 1, text[k].size(), files[k]);
+            bytes_done += maf.chain_bytes(chains[ci]);
+            if ((ci & 15) == 0 || ci + 1 == chains.size()) {
+                printf("\33[2K\r");
+                if (a.pos.size() > 2) printf("File %zu of %zu: ", fi, a.pos.size() - 1);
+                printf("%.2f / %.2f MB (%3.2f %%)\r", bytes_done / 1048576.0, maf.file_size() / 1048576.0, 100.0 * bytes_done / std::max<size_t>(1, maf.file_size()));
+                fflush(stdout);
+            }
+        }
+        for (auto &w : workers) w.join();
+        for (FILE *f : files) if (f) fclose(f);
+        total_cols += cols;
+    }
+    const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+    printf("\nDone!\n");
+    if (getenv("PCSF_HOST_STATS"))
+        printf("{\"columns\": %" PRId64 ", \"seconds\": %.3f, \"columns_per_s\": %.1f, \"threads\": %d, \"gpus\": %d, \"gpu_call_seconds_sum\": %.3f}\n",
+               total_cols, wall, total_cols / wall, threads, gpus, t_gpu);
+    // species of the model never seen in any alignment (build_tracks.hpp:487-504)
+    for (int s = 0; s < nl; ++s) {
+        bool any = false;
+        for (int t = 0; t < threads; ++t) any |= seen[t][s] != 0;
+        if (!any) printf("\033[33mWARNING: species %s from the model was never seen in any alignment.\033[0m\n", model.tree.labels[s].c_str());
+    }
+    for (pcsf_model *m : dev) pcsf_model_destroy(m);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- score-msa
+int main_score_msa(int argc, char **argv) {
+    const Args a = parse_args(argc, argv, {"strategy", "comp-phylo", "comp-anc", "comp-bls", "threads", "output", "mapping", "species", "gpus",
+                                           "genome-length", "coding-exons"});
+    if (a.pos.size() < 2) die("usage: phylocsf_b200 score-msa [OPTIONS] <model> <alignments>...");
+    const std::string strat = lower(a.str("strategy", "mle"));
+    pcsf_strategy strategy;
+    if (strat == "mle") strategy = PCSF_STRATEGY_MLE;
+    else if (strat == "fixed") strategy = PCSF_STRATEGY_FIXED;
+    else die("--strategy %s is not part of this tool (MLE and FIXED are)", strat.c_str());
+    const bool comp_phylo = a.boolean("comp-phylo", true), comp_anc = a.boolean("comp-anc", false), comp_bls = true;   // no --comp-bls in the reference
+    const int threads = std::max(1, a.integer("threads", (int)std::thread::hardware_concurrency()));
+    const int gpus = std::max(1, a.integer("gpus", 1));
+    const int workers_n = std::min(threads, 2 * gpus);      // the per-call batch is the unit of GPU work; parsing runs inside the workers
+
+    Model model;
+    load_model(model, a.pos[0], a.str("species"), a.str("mapping"));
+    const int nl = model.nl();
+    std::vector<pcsf_model *> dev(workers_n);
+    for (int t = 0; t < workers_n; ++t) dev[t] = create_device_model(model, t % gpus);
+
+    for (size_t fi = 1; fi < a.pos.size(); ++fi) {
+        const std::string &path = a.pos[fi];
+        std::string out_path = a.str("output");
+        if (out_path.empty()) out_path = path + ".scores";
+        else { create_directory(out_path); const size_t p = path.find_last_of('/'); out_path += "/" + (p == std::string::npos ? path : path.substr(p + 1)) + ".scores"; }
+        FILE *out = fopen(out_path.c_str(), "w");
+        if (!out) die("Error creating file '%s'!", out_path.c_str());
+        fprintf(out, "# PhyloCSF scores computed with PhyloCSF++ v1.2.0 (phylocsf_b200, B200-native likelihood core)\n");
+        fprintf(out, "seq\tstart\tend\tstrand");
+        if (comp_phylo) fprintf(out, "\tphylocsf-score");
+        if (comp_anc) fprintf(out, "\tanc-score");
+        if (comp_bls) fprintf(out, "\tbls-score");
+        fprintf(out, "\n");
+
+        MafFile maf(path, model, false, threads);
+        warn_unresolved(maf);
+        const std::vector<MafFile::Chain> &chains = maf.chains();
+        const size_t BATCH = 4096;
+        const size_t nbatch = (chains.size() + BATCH - 1) / BATCH;
+        OrderedSink sink;
+        sink.resize(nbatch);
+        std::atomic<size_t> next{0};
+        std::vector<std::thread> workers;
+        for (int t = 0; t < workers_n; ++t)
+            workers.emplace_back([&, t] {
+                Alignment aln;
+                for (size_t bi = next++; bi < nbatch; bi = next++) {
+                    const size_t c0 = bi * BATCH, c1 = std::min(chains.size(), c0 + BATCH);
+                    std::vector<uint8_t> blob;
+                    std::vector<int64_t> off, len;
+                    std::vector<std::string> head;
+                    for (size_t ci = c0; ci < c1; ++ci) {
+                        if (chains[ci].ref_id < 0) continue;
+                        maf.read_chain(chains[ci], aln, nullptr);
+                        off.push_back((int64_t)blob.size()); len.push_back(aln.L);
+                        blob.insert(blob.end(), aln.seqs.begin(), aln.seqs.end());
+                        char h[600];
+                        snprintf(h, sizeof h, "%s\t%" PRId64 "\t%" PRId64 "\t%c", aln.chrom.c_str(), aln.start_pos, aln.start_pos + aln.L - 1, aln.strand);
+                        head.push_back(h);
+                    }
+                    const int n = (int)off.size();
+                    std::vector<float> phylo(n, NAN), anc(n, NAN), bls(n, NAN);
+                    if (blob.empty()) blob.push_back('N');
+                    if (n > 0) {
+                        const pcsf_status st = pcsf_score_msa(dev[t], strategy, n, blob.data(), off.data(), len.data(), (comp_phylo || comp_anc) ? phylo.data() : nullptr,
+                                                              comp_anc ? anc.data() : nullptr, comp_bls ? bls.data() : nullptr);
+                        if (st == PCSF_ERR_BAD_CHAR) { fprintf(stderr, "%s\n", pcsf_last_error()); exit(37); }
+                        if (st != PCSF_OK) die("pcsf_score_msa: %s", pcsf_last_error());
+                    }
+                    std::string text;
+                    char v[64];
+                    for (int i = 0; i < n; ++i) {
+                        text += head[i];
+                        if (comp_phylo) { snprintf(v, sizeof v, "\t%.6f", phylo[i]); text += v; }
+                        if (comp_anc) { snprintf(v, sizeof v, "\t%.6f", anc[i]); text += v; }
+                        if (comp_bls) { snprintf(v, sizeof v, "\t%.6f", bls[i]); text += v; }
+                        text += "\n";
+                    }
+                    std::vector<std::string> one(1);
+                    one[0] = std::move(text);
+                    sink.put(bi, std::move(one));
+                }
+            });
+        for (size_t bi = 0; bi < nbatch; ++bi) {
+            std::vector<std::string> text = sink.take(bi);
+            fwrite(text[0].data(), 1, text[0].size(), out);
+        }
+        for (auto &w : workers) w.join();
+        fclose(out);
+    }
+    printf("Done!\n");
+    for (pcsf_model *m : dev) pcsf_model_destroy(m);
+    (void)nl;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------- dump-alignments
+// Test hook (no GPU needed): what the reader hands to the likelihood core, one line per alignment.
+int main_dump_alignments(int argc, char **argv) {
+    const Args a = parse_args(argc, argv, {"concatenate", "threads", "mapping", "species"});
+    if (a.pos.size() < 2) die("usage: phylocsf_b200 dump-alignments [--concatenate BOOL] [--threads INT] <model> <alignments>...");
+    Model model;
+    load_model(model, a.pos[0], a.str("species"), a.str("mapping"));
+    for (size_t fi = 1; fi < a.pos.size(); ++fi) {
+        MafFile maf(a.pos[fi], model, a.boolean("concatenate", true), std::max(1, a.integer("threads", 4)));
+        Alignment aln;
+        for (const MafFile::Chain &c : maf.chains()) {
+            maf.read_chain(c, aln, nullptr);
+            uint64_t h = 1469598103934665603ull;
+            for (uint8_t b : aln.seqs) { h ^= b; h *= 1099511628211ull; }
+            printf("%s\t%" PRId64 "\t%" PRId64 "\t%c\t%" PRId64 "\t%016" PRIx64 "\n", aln.chrom.c_str(), aln.start_pos, aln.chrom_len, aln.strand, aln.L, h);
+        }
+    }
+    return 0;
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    if (argc < 2 || !strcmp(argv[1], "--help") || !strcmp(argv[1], "-h")) {
+        printf("phylocsf_b200 — B200-native PhyloCSF++ likelihood core behind the reference's command line\n\n"
+               "  phylocsf_b200 build-tracks [--output-raw-phylo BOOL] [--power-threshold FLOAT] [--threads INT] [--gpus INT]\n"
+               "                             [--precision f64|tc5|f32] [--output DIR] [--mapping FILE] [--species LIST] <model> <maf>...\n"
+               "  phylocsf_b200 score-msa    [--strategy MLE|FIXED] [--comp-phylo BOOL] [--comp-anc BOOL] [--threads INT] [--gpus INT]\n"
+               "                             [--output DIR] [--mapping FILE] [--species LIST] <model> <maf>...\n");
+        return argc < 2 ? 1 : 0;
+    }
+    const std::string tool = argv[1];
+    if (tool == "build-tracks") return main_build_tracks(argc, argv);
+    if (tool == "score-msa") return main_score_msa(argc, argv);
+    if (tool == "dump-alignments") return main_dump_alignments(argc, argv);
+    die("unknown tool '%s' (build-tracks and score-msa are available)", tool.c_str());
+}

@@ -1,0 +1,133 @@
+"""The C++ host (phylocsfpp_b200/host -> bin/phylocsf_b200): its MAF reader against the Python mirror on the reference's
+fixtures and on a synthetic file with breakpoints, holes, reference gaps and unknown species (CPU), and the two tools end
+to end against the reference's golden outputs (GPU)."""
+import gzip
+import os
+import shutil
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from phylocsfpp_b200.maf import MafReader
+from phylocsfpp_b200.models import load_model
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "phylocsfpp_b200", "bin", "phylocsf_b200")
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+def _need_bin():
+    if not os.path.exists(BIN):
+        pytest.fail(f"{BIN} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+
+
+def _fnv(a: np.ndarray) -> str:
+    h = 1469598103934665603
+    for b in a.reshape(-1).tolist():
+        h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return "%016x" % h
+
+
+def _dump(model_arg, maf, concatenate, threads, species=""):
+    cmd = [BIN, "dump-alignments", "--concatenate", "1" if concatenate else "0", "--threads", str(threads)]
+    if species:
+        cmd += ["--species", species]
+    out = subprocess.run(cmd + [model_arg, maf], check=True, capture_output=True, text=True).stdout
+    return [ln.split("\t") for ln in out.splitlines()]
+
+
+def _gunzip(src, tmp_path):
+    dst = os.path.join(tmp_path, os.path.basename(src)[:-3])
+    with gzip.open(src, "rb") as fi, open(dst, "wb") as fo:
+        shutil.copyfileobj(fi, fo)
+    return dst
+
+
+def _compare(rows, alns, hash_limit=200000):
+    alns = [a for a in alns]
+    assert len(rows) == len(alns)
+    for r, a in zip(rows, alns):
+        assert r[0] == a.chrom and int(r[1]) == a.start_pos and int(r[2]) == a.chrom_len and r[3] == a.strand and int(r[4]) == a.L
+        if a.seqs.size <= hash_limit:
+            assert r[5] == _fnv(a.seqs)
+
+
+def test_reader_matches_mirror_on_reference_fixtures(golden_dir, tmp_path):
+    _need_bin()
+    G = os.path.join(golden_dir, "build-tracks")
+    maf = _gunzip(os.path.join(G, "galGal6_chr22_25_28_each_30k_bases.maf.gz"), str(tmp_path))
+    model = load_model(os.path.join(G, "53birds"))
+    ref = list(MafReader(maf, model.seqid_to_phyloid, model.nl, True, warn=False))
+    for threads in (1, 3, 8):
+        _compare(_dump(os.path.join(G, "53birds"), maf, True, threads), ref, hash_limit=10 ** 7 if threads == 1 else 0)
+    S = os.path.join(golden_dir, "score-msa")
+    model = load_model("100vertebrates")
+    maf = os.path.join(S, "chr22.50alignments.maf")
+    ref = list(MafReader(maf, model.seqid_to_phyloid, model.nl, False, warn=False))
+    _compare(_dump("100vertebrates", maf, False, 4), ref)
+
+
+def test_reader_synthetic_breakpoints_holes_gaps(tmp_path):
+    """2.3 M reference bases starting at 10 000: two 1 Mb breakpoints (the +2-base read-ahead and the rewind), a few holes,
+    1 % reference-gap columns, absent species, a --species reduction with rows of species outside the subset."""
+    _need_bin()
+    from make_synth_maf import write_synth_maf
+    model = load_model("12flies")
+    maf = os.path.join(str(tmp_path), "synth.maf")
+    info = write_synth_maf(maf, model, 2_300_000, seed=5, hole_p=1 / 4000.0)
+    assert info["blocks"] > 10000
+    ref = list(MafReader(maf, model.seqid_to_phyloid, model.nl, True, warn=False))
+    assert any(a.L > 900000 for a in ref) and len(ref) > 5
+    for threads in (1, 5):
+        _compare(_dump("12flies", maf, True, threads), ref, hash_limit=3_000_000 if threads == 5 else 0)
+    sub = "dmel,dsim,dyak,dpse"
+    msub = load_model("12flies", sub)
+    ref = list(MafReader(maf, msub.seqid_to_phyloid, msub.nl, False, warn=False))
+    rows = _dump("12flies", maf, False, 4, species=sub)
+    ref = [a for a in ref if a.L > 0 or a.chrom]
+    _compare(rows[:2000], ref[:2000])
+
+
+@pytest.mark.gpu
+def test_build_tracks_cli_golden(golden_dir, tmp_path):
+    """Config 1 through the command line tool: the reference's seven expected wig files, byte for byte (FP64 path), with
+    one and with several threads; the tcgen05 path within 1e-3 decibans of them."""
+    _need_bin()
+    G = os.path.join(golden_dir, "build-tracks")
+    maf = _gunzip(os.path.join(G, "galGal6_chr22_25_28_each_30k_bases.maf.gz"), str(tmp_path))
+    names = ["PhyloCSFpower.wig"] + [f"PhyloCSFRaw{s}{f}.wig" for s in "+-" for f in (1, 2, 3)]
+    for threads in (1, 4):
+        out = os.path.join(str(tmp_path), f"out{threads}")
+        subprocess.run([BIN, "build-tracks", "--threads", str(threads), "--output", out, os.path.join(G, "53birds"), maf], check=True,
+                       capture_output=True)
+        for n in names:
+            assert open(os.path.join(out, n), "rb").read() == gzip.open(os.path.join(G, n + ".gz"), "rb").read(), n
+    out = os.path.join(str(tmp_path), "out_tc5")
+    subprocess.run([BIN, "build-tracks", "--threads", "2", "--precision", "tc5", "--output", out, os.path.join(G, "53birds"), maf], check=True,
+                   capture_output=True)
+    for n in names:
+        a = open(os.path.join(out, n)).read().split("\n")
+        b = gzip.open(os.path.join(G, n + ".gz"), "rt").read().split("\n")
+        assert len(a) == len(b)
+        for x, y in zip(a, b):
+            if x != y:
+                assert not x.startswith("fixedStep") and abs(float(x) - float(y)) <= 0.0011, (n, x, y)
+
+
+@pytest.mark.gpu
+def test_score_msa_cli_golden(golden_dir, tmp_path):
+    _need_bin()
+    S = os.path.join(golden_dir, "score-msa")
+    maf = os.path.join(str(tmp_path), "chr22.50alignments.maf")
+    shutil.copy(os.path.join(S, "chr22.50alignments.maf"), maf)
+    out = os.path.join(str(tmp_path), "o")
+    subprocess.run([BIN, "score-msa", "--strategy", "fixed", "--comp-anc", "1", "--output", out, "100vertebrates", maf], check=True, capture_output=True)
+    ours = [ln.rstrip("\n").split("\t") for ln in open(os.path.join(out, "chr22.50alignments.maf.scores"))][2:]
+    gold = [ln.rstrip("\n").split("\t") for ln in open(os.path.join(S, "chr22.50alignments.fixed.scores"))][1:]
+    gold = [g for g in gold if not g[0].startswith("seq")]
+    assert len(ours) == len(gold)
+    for o, g in zip(ours, gold):
+        assert o[:4] == g[:4] and o[6] == g[6]
+        assert abs(float(o[4]) - float(g[4])) <= 1e-3 and abs(float(o[5]) - float(g[5])) <= 1e-3

@@ -91,6 +91,7 @@ public:
     struct Chain {
         std::vector<size_t> blocks;
         int64_t start_pos = 0, chrom_len = 0, keep_cols = -1;     // keep_cols >= 0: truncate to that many reference bases
+        int64_t ref_cols = 0;                                     // reference bases of the chain (before truncation)
         char strand = '+';
         std::string chrom;
         int ref_id = -1;
@@ -303,6 +304,7 @@ private:
             if (reached_bp && prev_cum >= cum_after_bp + 2) abort_next = true;
             if (abort_next && concatenate_) pos = saved_pos;
             if (reached_bp && prev_cum > cum_after_bp + 2) c.keep_cols = cum_after_bp + 2;
+            c.ref_cols = c.keep_cols >= 0 ? c.keep_cols : prev_cum;
             chains_.push_back(std::move(c));
         }
     }

@@ -81,6 +81,37 @@ struct OrderedSink {
     }
 };
 
+// Device models are pooled: two per GPU (one call can copy while the other computes); more host threads inside the library
+// would only contend for the device and the driver.
+struct ModelPool {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<pcsf_model *> free_models;
+    std::vector<pcsf_model *> all;
+    void add(pcsf_model *m) { free_models.push_back(m); all.push_back(m); }
+    pcsf_model *acquire() {
+        std::unique_lock<std::mutex> g(mu);
+        cv.wait(g, [&] { return !free_models.empty(); });
+        pcsf_model *m = free_models.back();
+        free_models.pop_back();
+        return m;
+    }
+    void release(pcsf_model *m) { { std::lock_guard<std::mutex> g(mu); free_models.push_back(m); } cv.notify_one(); }
+    void destroy() { for (pcsf_model *m : all) pcsf_model_destroy(m); all.clear(); free_models.clear(); }
+};
+
+// one pool per GPU, filled in parallel (model preparation is host work: eigensystem + all P(t) + uploads)
+void make_pools(const Model &model, int gpus, int per_gpu, std::vector<std::unique_ptr<ModelPool>> &pools) {
+    std::vector<pcsf_model *> ms((size_t)gpus * per_gpu);
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < ms.size(); ++i) th.emplace_back([&, i] { ms[i] = create_device_model(model, (int)(i / per_gpu)); });
+    for (auto &t : th) t.join();
+    for (int g = 0; g < gpus; ++g) {
+        pools.emplace_back(new ModelPool);
+        for (int k = 0; k < per_gpu; ++k) pools.back()->add(ms[(size_t)g * per_gpu + k]);
+    }
+}
+
 void warn_unresolved(const MafFile &maf) {
     for (const std::string &s : maf.unresolved())
         printf("\033[33mWARNING: Not able to match species %s in alignment file to model (Use `--mapping` to fix it)!\033[0m\n", s.c_str());
@@ -103,9 +134,10 @@ int main_build_tracks(int argc, char **argv) {
     Model model;
     load_model(model, a.pos[0], a.str("species"), a.str("mapping"));
     const int nl = model.nl();
-    std::vector<pcsf_model *> dev(threads);
-    for (int t = 0; t < threads; ++t) dev[t] = create_device_model(model, t % gpus);
+    std::vector<std::unique_ptr<ModelPool>> pools;
+    make_pools(model, gpus, 2, pools);
     std::vector<std::vector<uint8_t>> seen(threads, std::vector<uint8_t>(nl, 0));
+    double t_parse = 0.0, t_format = 0.0, t_scan = 0.0;
     static const char *kFrames[6] = {"+1", "+2", "+3", "-1", "-2", "-3"};
     int64_t total_cols = 0;
     double t_gpu = 0.0;
@@ -120,7 +152,9 @@ int main_build_tracks(int argc, char **argv) {
         } else {
             create_directory(out_dir);
         }
+        const auto s0 = std::chrono::steady_clock::now();
         MafFile maf(path, model, true, threads);
+        t_scan += std::chrono::duration<double>(std::chrono::steady_clock::now() - s0).count();
         warn_unresolved(maf);
         const std::vector<MafFile::Chain> &chains = maf.chains();
         FILE *files[7];
@@ -129,6 +163,18 @@ int main_build_tracks(int argc, char **argv) {
         for (int k = 0; k < 6; ++k) files[1 + k] = raw ? fopen((out_dir + "/PhyloCSFRaw" + kFrames[k] + ".wig").c_str(), mode) : nullptr;
         if (!files[0] || (raw && !files[1])) die("Error creating output files in '%s'!", out_dir.c_str());
 
+        // consecutive chains are scored in one library call (their columns concatenated; the windows that straddle two
+        // chains are computed and ignored): keeps the per-call cost off the many short chains of a gappy file
+        std::vector<std::pair<size_t, size_t>> groups;
+        {
+            const int64_t GROUP_COLS = 1 << 20;
+            size_t g0 = 0;
+            int64_t acc = 0;
+            for (size_t ci = 0; ci < chains.size(); ++ci) {
+                acc += chains[ci].ref_cols + 2;
+                if (acc >= GROUP_COLS || ci + 1 == chains.size() || ci + 1 - g0 >= 4096) { groups.emplace_back(g0, ci + 1); g0 = ci + 1; acc = 0; }
+            }
+        }
         OrderedSink sink;
         sink.resize(chains.size());
         std::atomic<size_t> next{0};
@@ -137,69 +183,101 @@ int main_build_tracks(int argc, char **argv) {
         std::vector<std::thread> workers;
         for (int t = 0; t < threads; ++t)
             workers.emplace_back([&, t] {
-                Alignment aln;
+                std::vector<Alignment> alns;
+                std::vector<uint8_t> mat;
                 std::vector<double> plus, minus, bls;
-                double my_gpu = 0.0;
-                for (size_t ci = next++; ci < chains.size(); ci = next++) {
-                    std::vector<std::string> text(7);
-                    maf.read_chain(chains[ci], aln, &seen[t]);
-                    const int64_t L = aln.L;
-                    if (L > 0) {
-                        plus.resize((size_t)std::max<int64_t>(L - 2, 0)); minus.resize(plus.size()); bls.resize((size_t)L);
-                        const auto g0 = std::chrono::steady_clock::now();
-                        const pcsf_status st = pcsf_tracks(dev[t], aln.seqs.data(), L, L, PCSF_TRACKS_BLS | (raw ? PCSF_TRACKS_SCORES : 0) | pflag,
+                double my_gpu = 0.0, my_parse = 0.0, my_fmt = 0.0;
+                auto now = [] { return std::chrono::steady_clock::now(); };
+                auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+                for (size_t gi = next++; gi < groups.size(); gi = next++) {
+                    const auto p0 = now();
+                    const size_t c0 = groups[gi].first, c1 = groups[gi].second;
+                    alns.resize(c1 - c0);
+                    int64_t Ltot = 0;
+                    std::vector<int64_t> col0(c1 - c0);
+                    for (size_t ci = c0; ci < c1; ++ci) {
+                        maf.read_chain(chains[ci], alns[ci - c0], &seen[t]);
+                        col0[ci - c0] = Ltot;
+                        Ltot += alns[ci - c0].L;
+                    }
+                    if (Ltot > 0) {
+                        const uint8_t *src = alns[0].seqs.data();
+                        if (c1 - c0 > 1) {
+                            mat.resize((size_t)nl * Ltot);
+                            for (size_t k = 0; k < c1 - c0; ++k)
+                                for (int s = 0; s < nl; ++s)
+                                    if (alns[k].L) memcpy(mat.data() + (size_t)s * Ltot + col0[k], alns[k].seqs.data() + (size_t)s * alns[k].L, (size_t)alns[k].L);
+                            src = mat.data();
+                        }
+                        plus.resize((size_t)std::max<int64_t>(Ltot - 2, 0)); minus.resize(plus.size()); bls.resize((size_t)Ltot);
+                        my_parse += secs(p0, now());
+                        ModelPool &pool = *pools[gi % gpus];
+                        pcsf_model *dm = pool.acquire();
+                        const auto g0 = now();
+                        const pcsf_status st = pcsf_tracks(dm, src, Ltot, Ltot, PCSF_TRACKS_BLS | (raw ? PCSF_TRACKS_SCORES : 0) | pflag,
                                                            plus.data(), minus.data(), bls.data(), nullptr, nullptr);
-                        my_gpu += std::chrono::duration<double>(std::chrono::steady_clock::now() - g0).count();
+                        my_gpu += secs(g0, now());
+                        pool.release(dm);
                         if (st == PCSF_ERR_BAD_CHAR) { fprintf(stderr, "%s\n", pcsf_last_error()); exit(37); }      // translation.hpp:46-51
                         if (st != PCSF_OK) die("pcsf_tracks: %s", pcsf_last_error());
-                        cols += L;
-                        char hdr[512];
-                        // power track (build_tracks.hpp:139-158)
-                        {
-                            std::string &o = text[0];
-                            const int64_t skip = mod3(3 - aln.start_pos);
-                            if (skip + 2 < L) {
-                                snprintf(hdr, sizeof hdr, "fixedStep chrom=%s start=%" PRId64 " step=3 span=3\n", aln.chrom.c_str(), aln.start_pos + skip);
-                                o += hdr;
-                            }
-                            for (int64_t pos = skip; pos + 2 < L; pos += 3) my_format(o, 4, (float)((bls[pos] + bls[pos + 1] + bls[pos + 2]) / 3.0));
-                        }
-                        // six raw tracks (build_tracks.hpp:160-216; frame arithmetic of update_seqs, parallel_file_reader.hpp:61-113)
-                        if (raw) {
-                            const float thr3 = threshold * 3;
-                            for (int k = 0; k < 6; ++k) {
-                                const bool fwd = k < 3;
-                                const int64_t frame = k % 3 + 1;
-                                int64_t o0, K;
-                                if (fwd) {
-                                    const int64_t skip = std::min<int64_t>(mod3(frame - aln.start_pos), L);
-                                    o0 = skip; K = (L - skip) / 3;
-                                } else {
-                                    const int64_t skip_r = std::min<int64_t>(mod3(frame - (aln.chrom_len - (aln.start_pos + L) + 2)), L);
-                                    o0 = (L - skip_r) % 3; K = (L - skip_r) / 3;
-                                }
-                                const std::vector<double> &src = fwd ? plus : minus;
-                                std::string &o = text[1 + k];
-                                int64_t prev = -4;
-                                for (int64_t xx = 0; xx < K; ++xx) {
-                                    const int64_t off = o0 + 3 * xx;
-                                    const float bsum = (float)(bls[off] + bls[off + 1] + bls[off + 2]);
-                                    if (bsum < thr3) continue;
-                                    const int64_t np = aln.start_pos + off;
-                                    if (prev + 3 != np) {
-                                        snprintf(hdr, sizeof hdr, "fixedStep chrom=%s start=%" PRId64 " step=3 span=3\n", aln.chrom.c_str(), np);
-                                        o += hdr;
-                                    }
-                                    prev = np;
-                                    my_format(o, 3, (float)src[off]);
-                                }
-                            }
-                        }
+                        cols += Ltot;
                     }
-                    sink.put(ci, std::move(text));
+                    const auto f0 = now();
+                    for (size_t ci = c0; ci < c1; ++ci) {
+                        const Alignment &aln = alns[ci - c0];
+                        const int64_t L = aln.L;
+                        std::vector<std::string> text(7);
+                        if (L > 0) {
+                            const double *pl = plus.data() + col0[ci - c0], *mi = minus.data() + col0[ci - c0], *bl = bls.data() + col0[ci - c0];
+                            char hdr[512];
+                            // power track (build_tracks.hpp:139-158)
+                            {
+                                std::string &o = text[0];
+                                const int64_t skip = mod3(3 - aln.start_pos);
+                                if (skip + 2 < L) {
+                                    snprintf(hdr, sizeof hdr, "fixedStep chrom=%s start=%" PRId64 " step=3 span=3\n", aln.chrom.c_str(), aln.start_pos + skip);
+                                    o += hdr;
+                                }
+                                for (int64_t pos = skip; pos + 2 < L; pos += 3) my_format(o, 4, (float)((bl[pos] + bl[pos + 1] + bl[pos + 2]) / 3.0));
+                            }
+                            // six raw tracks (build_tracks.hpp:160-216; frame arithmetic of update_seqs, parallel_file_reader.hpp:61-113)
+                            if (raw) {
+                                const float thr3 = threshold * 3;
+                                for (int k = 0; k < 6; ++k) {
+                                    const bool fwd = k < 3;
+                                    const int64_t frame = k % 3 + 1;
+                                    int64_t o0, K;
+                                    if (fwd) {
+                                        const int64_t skip = std::min<int64_t>(mod3(frame - aln.start_pos), L);
+                                        o0 = skip; K = (L - skip) / 3;
+                                    } else {
+                                        const int64_t skip_r = std::min<int64_t>(mod3(frame - (aln.chrom_len - (aln.start_pos + L) + 2)), L);
+                                        o0 = (L - skip_r) % 3; K = (L - skip_r) / 3;
+                                    }
+                                    const double *src_scores = fwd ? pl : mi;
+                                    std::string &o = text[1 + k];
+                                    int64_t prev = -4;
+                                    for (int64_t xx = 0; xx < K; ++xx) {
+                                        const int64_t off = o0 + 3 * xx;
+                                        const float bsum = (float)(bl[off] + bl[off + 1] + bl[off + 2]);
+                                        if (bsum < thr3) continue;
+                                        const int64_t np = aln.start_pos + off;
+                                        if (prev + 3 != np) {
+                                            snprintf(hdr, sizeof hdr, "fixedStep chrom=%s start=%" PRId64 " step=3 span=3\n", aln.chrom.c_str(), np);
+                                            o += hdr;
+                                        }
+                                        prev = np;
+                                        my_format(o, 3, (float)src_scores[off]);
+                                    }
+                                }
+                            }
+                        }
+                        sink.put(ci, std::move(text));
+                    }
+                    my_fmt += secs(f0, now());
                 }
                 std::lock_guard<std::mutex> g(gpu_time_mu);
-                t_gpu += my_gpu;
+                t_gpu += my_gpu; t_parse += my_parse; t_format += my_fmt;
             });
         size_t bytes_done = 0;
         for (size_t ci = 0; ci < chains.size(); ++ci) {
@@ -220,15 +298,16 @@ int main_build_tracks(int argc, char **argv) {
     const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
     printf("\nDone!\n");
     if (getenv("PCSF_HOST_STATS"))
-        printf("{\"columns\": %" PRId64 ", \"seconds\": %.3f, \"columns_per_s\": %.1f, \"threads\": %d, \"gpus\": %d, \"gpu_call_seconds_sum\": %.3f}\n",
-               total_cols, wall, total_cols / wall, threads, gpus, t_gpu);
+        printf("{\"columns\": %" PRId64 ", \"seconds\": %.3f, \"columns_per_s\": %.1f, \"threads\": %d, \"gpus\": %d, \"scan_seconds\": %.3f, "
+               "\"parse_seconds_sum\": %.3f, \"gpu_call_seconds_sum\": %.3f, \"format_seconds_sum\": %.3f}\n",
+               total_cols, wall, total_cols / wall, threads, gpus, t_scan, t_parse, t_gpu, t_format);
     // species of the model never seen in any alignment (build_tracks.hpp:487-504)
     for (int s = 0; s < nl; ++s) {
         bool any = false;
         for (int t = 0; t < threads; ++t) any |= seen[t][s] != 0;
         if (!any) printf("\033[33mWARNING: species %s from the model was never seen in any alignment.\033[0m\n", model.tree.labels[s].c_str());
     }
-    for (pcsf_model *m : dev) pcsf_model_destroy(m);
+    for (auto &p : pools) p->destroy();
     return 0;
 }
 
@@ -349,6 +428,35 @@ int main_dump_alignments(int argc, char **argv) {
     return 0;
 }
 
+// Test hook: the snprintf-free formatter against the reference's route on n pseudo-random floats + special values.
+int main_format_selftest(int argc, char **argv) {
+    const long n = argc > 2 ? atol(argv[2]) : 1000000;
+    uint64_t x = 0x9E3779B97F4A7C15ull;
+    long bad = 0;
+    std::string a, b;
+    auto check = [&](float v) {
+        for (int dec = 3; dec <= 4; ++dec) {
+            a.clear(); b.clear();
+            my_format(a, dec, v); my_format_printf(b, dec, v);
+            if (a != b) { if (bad < 10) printf("mismatch %.9g: '%s' vs '%s'\n", v, a.c_str(), b.c_str()); ++bad; }
+        }
+    };
+    const float special[] = {0.f, -0.f, 0.0625f, 0.1875f, -0.0004f, 0.0005f, 0.00049999f, 1e-30f, -1e-30f, 2.f, 10.f, 0.9995f, 0.99951f, 12345.6789f, -999.9995f,
+                             1e10f, 3.4e38f, 0.3125f, 0.4375f, 24.834f, 3.54f};
+    for (float v : special) check(v);
+    for (long i = 0; i < n; ++i) {
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+        const int e = (int)((x >> 40) % 40) - 20;                       // magnitudes 2^-20 .. 2^19
+        float v = (float)std::ldexp((double)(x & 0xffffff) / 16777216.0 + 0.5, e);
+        if (x & (1ull << 63)) v = -v;
+        check(v);
+        // exact ties at the rounding position
+        check((float)((double)((x >> 8) & 0xfffff) / 2048.0));
+    }
+    printf("%ld mismatches\n", bad);
+    return bad != 0;
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
@@ -364,5 +472,6 @@ int main(int argc, char **argv) {
     if (tool == "build-tracks") return main_build_tracks(argc, argv);
     if (tool == "score-msa") return main_score_msa(argc, argv);
     if (tool == "dump-alignments") return main_dump_alignments(argc, argv);
+    if (tool == "format-selftest") return main_format_selftest(argc, argv);
     die("unknown tool '%s' (build-tracks and score-msa are available)", tool.c_str());
 }

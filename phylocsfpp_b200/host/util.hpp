@@ -53,8 +53,8 @@ inline bool create_directory(const std::string &path) {
     return false;
 }
 
-// Appends my_fprintf(f, fmt, d) + '\n' to out.  decimals = 3 or 4.
-inline void my_format(std::string &out, int decimals, float d) {
+// Appends my_fprintf(f, fmt, d) + '\n' to out, decimals = 3 or 4, through snprintf (the reference's own route).
+inline void my_format_printf(std::string &out, int decimals, float d) {
     char buf[48];
     int n = snprintf(buf, sizeof buf, decimals == 3 ? "%.3f" : "%.4f", d);
     for (int i = n; i >= 0; --i) {
@@ -70,6 +70,30 @@ inline void my_format(std::string &out, int decimals, float d) {
     }
     out.append(buf);
     out.push_back('\n');
+}
+
+// Same text without snprintf.  A float has 24 significant bits and 10^3 = 2^3 * 125, 10^4 = 2^4 * 625 need 7 / 10 more,
+// so (double)d * 10^k is exact and nearbyint (ties to even, the default rounding mode) is exactly the decimal rounding
+// printf performs on the exact binary value.
+inline void my_format(std::string &out, int decimals, float d) {
+    const double scale = decimals == 3 ? 1000.0 : 10000.0;
+    const double r = __builtin_nearbyint((double)d * scale);
+    if (!(__builtin_fabs(r) < 9.0e15)) { my_format_printf(out, decimals, d); return; }
+    char buf[40];
+    char *e = buf + sizeof buf;
+    char *p = e;
+    *--p = '\n';
+    uint64_t q = (uint64_t)__builtin_fabs(r);
+    const uint64_t iscale = decimals == 3 ? 1000 : 10000;
+    uint64_t frac = q % iscale, ip = q / iscale;
+    // fractional digits, trailing zeros cut but one digit kept
+    int nd = decimals;
+    while (nd > 1 && frac % 10 == 0) { frac /= 10; --nd; }
+    for (int i = 0; i < nd; ++i) { *--p = (char)('0' + frac % 10); frac /= 10; }
+    *--p = '.';
+    do { *--p = (char)('0' + ip % 10); ip /= 10; } while (ip);
+    if (__builtin_signbit(r)) *--p = '-';
+    out.append(p, (size_t)(e - p));
 }
 
 }  // namespace host

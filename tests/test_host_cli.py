@@ -90,6 +90,14 @@ def test_reader_synthetic_breakpoints_holes_gaps(tmp_path):
     _compare(rows[:2000], ref[:2000])
 
 
+def test_wig_number_formatting_matches_printf():
+    """my_fprintf (reference src/common.hpp:48-68) re-implemented without snprintf: identical text on 2 M pseudo-random
+    floats, exact rounding ties and special values."""
+    _need_bin()
+    r = subprocess.run([BIN, "format-selftest", "1000000"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip().endswith("0 mismatches"), r.stdout[-2000:]
+
+
 @pytest.mark.gpu
 def test_build_tracks_cli_golden(golden_dir, tmp_path):
     """Config 1 through the command line tool: the reference's seven expected wig files, byte for byte (FP64 path), with

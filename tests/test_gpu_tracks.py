@@ -280,3 +280,20 @@ def test_tcgen05_path_properties_at_scale():
     assert np.abs(f64["minus"][0::3][:idx.size] - a["minus"][idx]).max() <= 3e-4
     assert np.isfinite(a["plus"]).all() and np.isfinite(a["minus"]).all()
     dm.close()
+
+
+@pytest.mark.parametrize("species", ["dmel,dsim", "dmel,dsim,dyak", "dmel,dsim,dyak,dpse,dvir"])
+def test_tcgen05_path_tiny_trees(species):
+    """--species reductions down to two leaves (the whole tree is one cherry: no GEMM step at all), three (one step)
+    and five; also alignments shorter than one codon window."""
+    model = load_model("12flies", species)
+    dm = capi.DeviceModel(model)
+    for L in (0, 1, 2, 3, 4, 700):
+        seqs = random_alignment(model.nl, L, seed=31 + L, gap=0.3, conserve=0.6)
+        f64 = dm.tracks(seqs)
+        t5 = dm.tracks(seqs, tc5=True)
+        assert t5["plus"].shape == f64["plus"].shape
+        if L > 2:
+            assert max(np.abs(t5["plus"] - f64["plus"]).max(), np.abs(t5["minus"] - f64["minus"]).max()) <= 2e-4
+        assert np.array_equal(t5["bls"], f64["bls"])
+    dm.close()

@@ -13,7 +13,10 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def write_synth_maf(path, model, ncols, seed=1, start0=10000, mean_block=120, hole_p=1 / 400.0, ref_gap=0.01, alien_p=0.02):
+def write_synth_maf(path, model, ncols, seed=1, start0=10000, mean_block=120, hole_p=1 / 400.0, ref_gap=0.01, alien_p=0.02,
+                    loguniform_blocks=None):
+    """loguniform_blocks=(lo, hi): block lengths log-uniform in [lo, hi] and a hole after every block (BASELINE config 5:
+    every block is its own alignment)."""
     import torch
     from phylocsfpp_b200.models import sequence_name_mapping
     from phylocsfpp_b200.synth import synth_alignment
@@ -27,8 +30,15 @@ def write_synth_maf(path, model, ncols, seed=1, start0=10000, mean_block=120, ho
         alts = sequence_name_mapping.get(label, [])
         names.append(alts[0] if alts else label)
     src_size = start0 + ncols + ncols // 100 + 400000
-    cuts = np.flatnonzero(rng.random(ncols) < 1.0 / mean_block)
-    cuts = np.unique(np.concatenate([[0], cuts, [ncols]]))
+    if loguniform_blocks:
+        lo, hi = loguniform_blocks
+        lens = np.exp(rng.uniform(np.log(lo), np.log(hi), size=int(ncols / lo) + 1)).astype(np.int64)
+        cuts = np.concatenate([[0], np.cumsum(lens)])
+        cuts = np.unique(np.concatenate([cuts[cuts < ncols], [ncols]]))
+        hole_p = 1.1
+    else:
+        cuts = np.flatnonzero(rng.random(ncols) < 1.0 / mean_block)
+        cuts = np.unique(np.concatenate([[0], cuts, [ncols]]))
     pos = start0
     n_blocks = 0
     with open(path, "wb") as fh:
@@ -67,4 +77,5 @@ def write_synth_maf(path, model, ncols, seed=1, start0=10000, mean_block=120, ho
 if __name__ == "__main__":
     from phylocsfpp_b200.models import load_model
     m = load_model(sys.argv[1])
-    print(write_synth_maf(sys.argv[3], m, int(sys.argv[2]), seed=int(sys.argv[4]) if len(sys.argv) > 4 else 1))
+    kw = dict(loguniform_blocks=(30, 600)) if os.environ.get("PCSF_SYNTH_SINGLE_BLOCKS") else {}
+    print(write_synth_maf(sys.argv[3], m, int(sys.argv[2]), seed=int(sys.argv[4]) if len(sys.argv) > 4 else 1, **kw))

@@ -8,7 +8,9 @@ chain cut into batches of --cols columns (100 M columns = 12 such batches; every
 
   value  columns/s with the batch resident in HBM (device-pointer C-ABI, CUDA events, max over ranks)
   e2e    columns/s through the host-buffer C-ABI call (pcsf_tracks): pinned host input, H2D, kernels, D2H
-  --impl reference   the CPU path (oracle port of the reference, all host cores) on a bounded sample
+  --impl reference   the reference's own CPU implementation (oracle/_ref/phylocsf_ref = its unmodified sources compiled
+                     against the GSL shim, OpenMP over all host cores; the oracle port only if that binary is missing),
+                     MAF file -> 7 wig files on a bounded sample of the same workload
 
 Launch: python bench.py --gpus N --steps K --warmup W   (N > 1: under torch.distributed.run, one rank per GPU).
 """
@@ -77,6 +79,46 @@ def cpu_columns_per_sec(model_name, seqs_host: np.ndarray, ncores: int, pool=Non
     return S / dt, dt
 
 
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "phylocsf_ref")
+
+
+def ref_sample_shape(ncores: int, per_step: bool):
+    """(chains, columns per chain) of the CPU sample: chains are the reference's unit of parallel work (a reader job owns the
+    chains that start in its byte range, parallel_file_reader.hpp:281-350), so the sample is cut into 4 (2) chains per core;
+    3000-4000 columns per chain keep the per-chain model instantiation (instance.hpp:449-646) near 10 % as on real chains."""
+    return (2 * ncores, 3000) if per_step else (4 * ncores, 4000)
+
+
+class RefSample:
+    """The first S columns of the workload written as a MAF file (tmpfs when available) for the reference binary."""
+
+    def __init__(self, model, mat: np.ndarray, chains: int, chain_cols: int):
+        import tempfile
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from make_synth_maf import write_synth_maf
+        self.S = chains * chain_cols
+        base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+        self.dir = tempfile.mkdtemp(prefix="pcsf_ref_", dir=base)
+        self.maf = os.path.join(self.dir, "sample.maf")
+        self.info = write_synth_maf(self.maf, model, self.S, seed=7, mat=mat, chain_cols=chain_cols, hole_p=0.0, ref_gap=0.0, alien_p=0.0)
+
+    def run(self, model_name: str, threads: int) -> float:
+        """One build-tracks run of the reference (power + 6 raw tracks); returns seconds."""
+        import shutil
+        out = os.path.join(self.dir, "out")
+        shutil.rmtree(out, ignore_errors=True)
+        t0 = time.perf_counter()
+        subprocess.run([REF_BIN, "build-tracks", "--threads", str(threads), "--output", out, model_name, self.maf], check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        dt = time.perf_counter() - t0
+        assert os.path.getsize(os.path.join(out, "PhyloCSFRaw+1.wig")) > 0
+        return dt
+
+    def close(self):
+        import shutil
+        shutil.rmtree(self.dir, ignore_errors=True)
+
+
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -121,6 +163,7 @@ def main():
     ap.add_argument("--cols", type=int, default=1 << 23, help="alignment columns per step (per GPU)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="columns of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-port", action="store_true", help="time the oracle port instead of the reference binary on the CPU legs")
     ap.add_argument("--no-dedup", action="store_true")
     ap.add_argument("--precision", default="tc5", choices=["f64", "f32", "tc5"],
                     help="tc5: tcgen05/TMEM split-TF32 path (fastest path inside the 1e-3 deciban contract); "
@@ -139,31 +182,47 @@ def main():
                 f"batches of {args.cols} columns (100M-column chain = {-(-100_000_000 // args.cols)} batches)")
 
     if args.impl == "reference":
-        # rank 0 only: the reference's CPU algorithm (oracle port) on a bounded sample per step
+        # rank 0 only: the reference's own CPU implementation on a bounded sample per step
         if rank != 0:
             return
-        import multiprocessing as mp
         import torch
         from phylocsfpp_b200.synth import synth_alignment
-        S = args.cpu_sample or 6000 * ncores
-        seqs = synth_alignment(model, S, seed=1234, device="cpu")[:, :S].numpy()
-        pool = mp.get_context("fork").Pool(ncores, initializer=_cpu_init, initargs=(args.model,))
-        pool.map(_cpu_chunk, [np.ascontiguousarray(seqs[:, :64])] * ncores)
-        for _ in range(args.warmup):
-            cpu_columns_per_sec(args.model, seqs, ncores, pool)
-        t = 0.0
-        for _ in range(args.steps):
-            t += cpu_columns_per_sec(args.model, seqs, ncores, pool)[1]
-        pool.close()
+        if os.path.exists(REF_BIN) and not args.cpu_port:
+            chains, chain_cols = ref_sample_shape(ncores, per_step=True)
+            S = args.cpu_sample or chains * chain_cols
+            chains = max(1, S // chain_cols)
+            seqs = synth_alignment(model, chains * chain_cols, seed=1234, device="cpu")[:, :chains * chain_cols].numpy()
+            smp = RefSample(model, seqs, chains, chain_cols)
+            S = smp.S
+            for _ in range(args.warmup):
+                smp.run(args.model, ncores)
+            t = sum(smp.run(args.model, ncores) for _ in range(args.steps))
+            smp.close()
+            kind = "reference"
+            sample = (f"{S} columns per step of the same synthetic workload as a MAF file of {chains} chains x {chain_cols} columns "
+                      f"({smp.info['blocks']} blocks, {smp.info['bytes']} bytes, tmpfs), the reference's unmodified build-tracks "
+                      f"(oracle/_ref, GSL shim, -O3 -fopenmp) --threads {ncores}: MAF parse + 6 raw tracks + power track + wig text")
+        else:
+            import multiprocessing as mp
+            S = args.cpu_sample or 6000 * ncores
+            seqs = synth_alignment(model, S, seed=1234, device="cpu")[:, :S].numpy()
+            pool = mp.get_context("fork").Pool(ncores, initializer=_cpu_init, initargs=(args.model,))
+            pool.map(_cpu_chunk, [np.ascontiguousarray(seqs[:, :64])] * ncores)
+            for _ in range(args.warmup):
+                cpu_columns_per_sec(args.model, seqs, ncores, pool)
+            t = 0.0
+            for _ in range(args.steps):
+                t += cpu_columns_per_sec(args.model, seqs, ncores, pool)[1]
+            pool.close()
+            kind = "port"
+            sample = f"{S} columns per step of the same synthetic workload, oracle port of the reference path, {ncores} processes"
         v = S * args.steps / t
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "sample_columns_per_step": S, "model": args.model},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": ncores, "kind": "port",
-                             "sample": f"{S} columns per step of the same synthetic workload, oracle port of the reference path, "
-                                       f"{ncores} processes"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": ncores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}))
         return
@@ -325,11 +384,24 @@ def main():
             "other_precisions": other,
         }
         if world == 1 and not args.no_cpu_baseline:
-            S = args.cpu_sample or 3000 * ncores
-            v, dt = cpu_columns_per_sec(args.model, seqs[:, :S].cpu().numpy(), ncores)
-            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": ncores, "kind": "port", "seconds": dt,
-                                   "sample": f"first {S} columns of the step's batch, oracle port of the reference path, "
-                                             f"{ncores} processes"}
+            if os.path.exists(REF_BIN) and not args.cpu_port:
+                chains, chain_cols = ref_sample_shape(ncores, per_step=False)
+                if args.cpu_sample:
+                    chains = max(1, args.cpu_sample // chain_cols)
+                smp = RefSample(model, seqs[:, :chains * chain_cols].cpu().numpy(), chains, chain_cols)
+                dt = smp.run(args.model, ncores)
+                smp.close()
+                out["cpu_baseline"] = {
+                    "value": smp.S / dt, "unit": UNIT, "cores": ncores, "kind": "reference", "seconds": dt,
+                    "sample": f"first {smp.S} columns of the step's batch as a MAF file of {chains} chains x {chain_cols} columns "
+                              f"({smp.info['blocks']} blocks, tmpfs), the reference's unmodified build-tracks (oracle/_ref, GSL shim, "
+                              f"-O3 -fopenmp) --threads {ncores}: MAF parse + 6 raw tracks + power track + wig text"}
+            else:
+                S = args.cpu_sample or 3000 * ncores
+                v, dt = cpu_columns_per_sec(args.model, seqs[:, :S].cpu().numpy(), ncores)
+                out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": ncores, "kind": "port", "seconds": dt,
+                                       "sample": f"first {S} columns of the step's batch, oracle port of the reference path, "
+                                                 f"{ncores} processes"}
         print(json.dumps(out), flush=True)
     dm.close()
     if world > 1:

@@ -14,15 +14,20 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
 def write_synth_maf(path, model, ncols, seed=1, start0=10000, mean_block=120, hole_p=1 / 400.0, ref_gap=0.01, alien_p=0.02,
-                    loguniform_blocks=None):
+                    loguniform_blocks=None, mat=None, chain_cols=None):
     """loguniform_blocks=(lo, hi): block lengths log-uniform in [lo, hi] and a hole after every block (BASELINE config 5:
-    every block is its own alignment)."""
+    every block is its own alignment).  mat: write these [nl, >=ncols] ASCII columns instead of generating them.
+    chain_cols: additionally force a block boundary and a hole every chain_cols columns (bounded chains = units of work for
+    the reference's job-parallel reader)."""
     import torch
     from phylocsfpp_b200.models import sequence_name_mapping
     from phylocsfpp_b200.synth import synth_alignment
     rng = np.random.default_rng(seed)
-    dev = "cuda" if torch.cuda.is_available() and os.environ.get("PCSF_SYNTH_CPU") is None else "cpu"
-    mat = synth_alignment(model, ncols, seed=seed, device=dev)[:, :ncols].cpu().numpy()
+    if mat is None:
+        dev = "cuda" if torch.cuda.is_available() and os.environ.get("PCSF_SYNTH_CPU") is None else "cpu"
+        mat = synth_alignment(model, ncols, seed=seed, device=dev)[:, :ncols].cpu().numpy()
+    else:
+        mat = np.ascontiguousarray(mat[:, :ncols])
     nl = model.nl
     names = []
     for i in range(nl):
@@ -39,6 +44,10 @@ def write_synth_maf(path, model, ncols, seed=1, start0=10000, mean_block=120, ho
     else:
         cuts = np.flatnonzero(rng.random(ncols) < 1.0 / mean_block)
         cuts = np.unique(np.concatenate([[0], cuts, [ncols]]))
+    forced = set()
+    if chain_cols:
+        forced = set(range(chain_cols, ncols, chain_cols))
+        cuts = np.unique(np.concatenate([cuts, np.fromiter(forced, np.int64, len(forced))]))
     pos = start0
     n_blocks = 0
     with open(path, "wb") as fh:
@@ -69,7 +78,7 @@ def write_synth_maf(path, model, ncols, seed=1, start0=10000, mean_block=120, ho
             fh.write(b"\n")
             pos += size
             n_blocks += 1
-            if rng.random() < hole_p:
+            if rng.random() < hole_p or int(b) in forced:
                 pos += int(rng.integers(1, 301))
     return dict(columns=int(ncols), blocks=n_blocks, bytes=os.path.getsize(path))
 

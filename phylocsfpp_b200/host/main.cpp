@@ -9,12 +9,14 @@
 // their GPU (thread t -> GPU t mod --gpus) and format the text; a writer appends the results in file order, so the
 // output does not depend on the thread or GPU count (the reference merges its per-job files in job order,
 // build_tracks.hpp:27-53,245-259).
-// Not in this tool: --output-phylo / --output-regions (PhyloCSF-HMM smoothing), the OMEGA and FIXED_MEAN strategies.
+// --output-phylo / --output-regions: the PhyloCSF-HMM smoothing of the raw tracks stays on the host (hmm.hpp).
+// Not in this tool: the OMEGA and FIXED_MEAN strategies.
 #include <cinttypes>
 #include <chrono>
 #include <condition_variable>
 #include <cmath>
 
+#include "hmm.hpp"
 #include "maf.hpp"
 
 using namespace host;
@@ -122,9 +124,17 @@ int main_build_tracks(int argc, char **argv) {
     const Args a = parse_args(argc, argv, {"output-raw-phylo", "output-phylo", "output-regions", "power-threshold", "genome-length", "coding-exons",
                                            "threads", "output", "mapping", "species", "gpus", "precision"});
     if (a.pos.size() < 2) die("usage: phylocsf_b200 build-tracks [OPTIONS] <model> <alignments>...");
-    if (a.boolean("output-phylo", false) || a.boolean("output-regions", false))
-        die("--output-phylo / --output-regions (PhyloCSF-HMM smoothing) are not part of this tool");
-    const bool raw = a.boolean("output-raw-phylo", true);
+    const bool keep_raw = a.boolean("output-raw-phylo", true);
+    const bool smooth = a.boolean("output-phylo", false), regions = a.boolean("output-regions", false);
+    if ((smooth || regions) && (!a.has("genome-length") || !a.has("coding-exons"))) {          // build_tracks.hpp:420-432
+        printf("\033[31m%s\n\033[0m", smooth ? "For smoothened tracks (--output-phylo) you need to provide --genome-length and --coding-exons."
+                                             : "To generate bed file of potential protein coding regions, you need to provide --genome-length and --coding-exons.");
+        return -1;
+    }
+    const bool raw = keep_raw || smooth || regions;          // the raw tracks are the HMM's input (build_tracks.hpp:109,248)
+    Hmm hmm_model{};
+    if (smooth || regions)          // models.hpp:1760-1764 (the reference estimates only for --output-phylo and leaves the HMM unset for regions alone)
+        hmm_model = coding_hmm(estimate_hmm_params(a.str("coding-exons"), (uint32_t)strtoull(a.str("genome-length").c_str(), nullptr, 10)));
     // the reference reads --power-threshold with get_bool (build_tracks.hpp:416-417): anything but 1/true/one gives 0
     const float threshold = a.has("power-threshold") ? (a.boolean("power-threshold", false) ? 1.0f : 0.0f) : 0.1f;
     const int threads = std::max(1, a.integer("threads", (int)std::thread::hardware_concurrency()));
@@ -294,6 +304,24 @@ int main_build_tracks(int argc, char **argv) {
         for (auto &w : workers) w.join();
         for (FILE *f : files) if (f) fclose(f);
         total_cols += cols;
+        // PhyloCSF-HMM over the text of the six raw tracks (build_tracks.hpp:262-348), one thread per track
+        if (smooth || regions) {
+            printf("\33[2K\rSmoothing scores and/or computing coding-regions ...\r");
+            fflush(stdout);
+            std::vector<std::thread> sm;
+            for (int k = 0; k < 6; ++k)
+                sm.emplace_back([&, k] {
+                    const std::string rawp = out_dir + "/PhyloCSFRaw" + kFrames[k] + ".wig";
+                    FILE *fw = smooth ? fopen((out_dir + "/PhyloCSF" + kFrames[k] + ".wig").c_str(), "w") : nullptr;
+                    FILE *fb = regions ? fopen((out_dir + "/PhyloCSF" + kFrames[k] + "Regions.bed").c_str(), "w") : nullptr;
+                    if ((smooth && !fw) || (regions && !fb)) die("Error creating output files in '%s'!", out_dir.c_str());
+                    hmm_smooth_file(hmm_model, rawp, kFrames[k][0], fw, fb);
+                    if (fw) fclose(fw);
+                    if (fb) fclose(fb);
+                    if (!keep_raw) unlink(rawp.c_str());
+                });
+            for (auto &t : sm) t.join();
+        }
     }
     const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
     printf("\nDone!\n");
@@ -428,6 +456,29 @@ int main_dump_alignments(int argc, char **argv) {
     return 0;
 }
 
+// Test hook (no GPU needed): the PhyloCSF-HMM stage alone on existing raw tracks.
+int main_smooth_tracks(int argc, char **argv) {
+    const Args a = parse_args(argc, argv, {"genome-length", "coding-exons", "output-phylo", "output-regions", "print-hmm"});
+    if (a.pos.size() != 2 || !a.has("genome-length") || !a.has("coding-exons"))
+        die("usage: phylocsf_b200 smooth-tracks --genome-length INT --coding-exons FILE [--output-phylo BOOL] [--output-regions BOOL] <raw dir> <out dir>");
+    const HmmParams hp = estimate_hmm_params(a.str("coding-exons"), (uint32_t)strtoull(a.str("genome-length").c_str(), nullptr, 10));
+    const Hmm h = coding_hmm(hp);
+    if (a.boolean("print-hmm", false)) {
+        printf("coding_prior %.17g\ncoding_codons %.17g\n", hp.coding_prior, hp.coding_codons);
+        for (int j = 0; j < 3; ++j) printf("nc %d weight %.17g codons %.17g\n", j, hp.nc_weight[j], hp.nc_codons[j]);
+    }
+    create_directory(a.pos[1]);
+    static const char *kFrames[6] = {"+1", "+2", "+3", "-1", "-2", "-3"};
+    for (int k = 0; k < 6; ++k) {
+        FILE *fw = a.boolean("output-phylo", true) ? fopen((a.pos[1] + "/PhyloCSF" + kFrames[k] + ".wig").c_str(), "w") : nullptr;
+        FILE *fb = a.boolean("output-regions", true) ? fopen((a.pos[1] + "/PhyloCSF" + kFrames[k] + "Regions.bed").c_str(), "w") : nullptr;
+        hmm_smooth_file(h, a.pos[0] + "/PhyloCSFRaw" + kFrames[k] + ".wig", kFrames[k][0], fw, fb);
+        if (fw) fclose(fw);
+        if (fb) fclose(fb);
+    }
+    return 0;
+}
+
 // Test hook: the snprintf-free formatter against the reference's route on n pseudo-random floats + special values.
 int main_format_selftest(int argc, char **argv) {
     const long n = argc > 2 ? atol(argv[2]) : 1000000;
@@ -462,7 +513,8 @@ int main_format_selftest(int argc, char **argv) {
 int main(int argc, char **argv) {
     if (argc < 2 || !strcmp(argv[1], "--help") || !strcmp(argv[1], "-h")) {
         printf("phylocsf_b200 — B200-native PhyloCSF++ likelihood core behind the reference's command line\n\n"
-               "  phylocsf_b200 build-tracks [--output-raw-phylo BOOL] [--power-threshold FLOAT] [--threads INT] [--gpus INT]\n"
+               "  phylocsf_b200 build-tracks [--output-raw-phylo BOOL] [--output-phylo BOOL] [--output-regions BOOL] [--genome-length INT]\n"
+               "                             [--coding-exons FILE] [--power-threshold FLOAT] [--threads INT] [--gpus INT]\n"
                "                             [--precision f64|tc5|f32] [--output DIR] [--mapping FILE] [--species LIST] <model> <maf>...\n"
                "  phylocsf_b200 score-msa    [--strategy MLE|FIXED] [--comp-phylo BOOL] [--comp-anc BOOL] [--threads INT] [--gpus INT]\n"
                "                             [--output DIR] [--mapping FILE] [--species LIST] <model> <maf>...\n");
@@ -470,6 +522,7 @@ int main(int argc, char **argv) {
     }
     const std::string tool = argv[1];
     if (tool == "build-tracks") return main_build_tracks(argc, argv);
+    if (tool == "smooth-tracks") return main_smooth_tracks(argc, argv);
     if (tool == "score-msa") return main_score_msa(argc, argv);
     if (tool == "dump-alignments") return main_dump_alignments(argc, argv);
     if (tool == "format-selftest") return main_format_selftest(argc, argv);

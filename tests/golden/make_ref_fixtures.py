@@ -10,6 +10,10 @@ Fixtures (what each one pins that the reference's own goldens do not):
   tracks12   build-tracks, 12flies, 15 000 reference columns starting at 992 001: a chain that crosses the 1 Mb
              BREAKPOINT_POS (+2-base read-ahead, cursor rewind), holes, reference-gap columns, absent species, rows of an
              unknown species, soft-masked blocks -> 7 wig files
+  smooth53   build-tracks --output-phylo 1 --output-regions 1 on the reference's own example MAF (53birds) with coding exons
+             taken from example/galGal6_chr22_25_28_subset_ncbiRefSeq.gtf by the README's awk line (README.rst:124; the
+             exon list its tests.sh names is not shipped) -> 6 smoothed wigs + 6 region BED files
+  smooth12   the same on tracks12 with tests/util.py:write_synthetic_exons (46 000 exons: gap subsampling path)
   msa29      score-msa, 29mammals reduced with --species to 12 leaves, 60 single-block alignments of 30..600 columns
              (BASELINE config 5 shape), strategies fixed / mle (--comp-anc 1) and omega -> .scores files
 """
@@ -54,6 +58,29 @@ def main():
         gz(maf, os.path.join(OUT, "tracks12.maf.gz"))
         for n in ["PhyloCSFpower.wig"] + [f"PhyloCSFRaw{s}{f}.wig" for s in "+-" for f in (1, 2, 3)]:
             gz(os.path.join(tmp, "t12", n), os.path.join(OUT, "tracks12." + n + ".gz"))
+        # ---- smooth53 / smooth12
+        from tests.util import write_synthetic_exons
+        G = os.path.join(HERE, "build-tracks")
+        maf53 = os.path.join(tmp, "in53.maf")
+        with gzip.open(os.path.join(G, "galGal6_chr22_25_28_each_30k_bases.maf.gz"), "rb") as fi, open(maf53, "wb") as fo:
+            shutil.copyfileobj(fi, fo)
+        exons = os.path.join(tmp, "smooth53.coding_exons.txt")
+        with open(exons, "w") as fo:
+            for ln in open("/root/reference/example/galGal6_chr22_25_28_subset_ncbiRefSeq.gtf"):
+                f = ln.rstrip("\n").split("\t")
+                if len(f) > 7 and f[2] == "CDS":
+                    fo.write("\t".join([f[0], f[6], f[7], f[3], f[4]]) + "\n")
+        gz(exons, os.path.join(OUT, "smooth53.coding_exons.txt.gz"))
+        ref("build-tracks", "--threads", "8", "--output-phylo", "1", "--output-regions", "1", "--genome-length", "1065365434", "--coding-exons", exons,
+            "--output", os.path.join(tmp, "s53"), os.path.join(G, "53birds"), maf53)
+        exons12 = os.path.join(tmp, "exons12.txt")
+        write_synthetic_exons(exons12)
+        ref("build-tracks", "--threads", "4", "--output-phylo", "1", "--output-regions", "1", "--genome-length", "400000000", "--coding-exons", exons12,
+            "--output", os.path.join(tmp, "s12"), "12flies", os.path.join(tmp, "tracks12.maf"))
+        for tag, d in (("smooth53", "s53"), ("smooth12", "s12")):
+            for k in ("+1", "+2", "+3", "-1", "-2", "-3"):
+                gz(os.path.join(tmp, d, f"PhyloCSF{k}.wig"), os.path.join(OUT, f"{tag}.PhyloCSF{k}.wig.gz"))
+                gz(os.path.join(tmp, d, f"PhyloCSF{k}Regions.bed"), os.path.join(OUT, f"{tag}.PhyloCSF{k}Regions.bed.gz"))
         # ---- msa29
         maf = os.path.join(tmp, "msa29.maf")
         print(write_synth_maf(maf, load_model("29mammals"), 14000, seed=12, loguniform_blocks=(30, 600), alien_p=0.05))

@@ -98,6 +98,65 @@ def test_wig_number_formatting_matches_printf():
     assert r.returncode == 0 and r.stdout.strip().endswith("0 mismatches"), r.stdout[-2000:]
 
 
+FRAMES6 = ["+1", "+2", "+3", "-1", "-2", "-3"]
+
+
+def _smooth_inputs(golden_dir, tmp_path, tag):
+    """raw-track directory + exon list + genome length of the two smoothing fixtures of tests/golden/ref-generated/."""
+    from tests.util import write_synthetic_exons
+    R = os.path.join(golden_dir, "ref-generated")
+    raw = os.path.join(str(tmp_path), "raw_" + tag)
+    os.makedirs(raw, exist_ok=True)
+    exons = os.path.join(str(tmp_path), tag + ".exons.txt")
+    if tag == "smooth53":
+        for k in FRAMES6:
+            _gunzip(os.path.join(golden_dir, "build-tracks", f"PhyloCSFRaw{k}.wig.gz"), raw)
+        with gzip.open(os.path.join(R, "smooth53.coding_exons.txt.gz"), "rb") as fi, open(exons, "wb") as fo:
+            shutil.copyfileobj(fi, fo)
+        return raw, exons, "1065365434"
+    for k in FRAMES6:
+        with gzip.open(os.path.join(R, f"tracks12.PhyloCSFRaw{k}.wig.gz"), "rb") as fi, open(os.path.join(raw, f"PhyloCSFRaw{k}.wig"), "wb") as fo:
+            shutil.copyfileobj(fi, fo)
+    write_synthetic_exons(exons)
+    return raw, exons, "400000000"
+
+
+def _assert_smoothed(out, golden_dir, tag):
+    R = os.path.join(golden_dir, "ref-generated")
+    for k in FRAMES6:
+        assert open(os.path.join(out, f"PhyloCSF{k}.wig"), "rb").read() == gzip.open(os.path.join(R, f"{tag}.PhyloCSF{k}.wig.gz"), "rb").read(), k
+        assert open(os.path.join(out, f"PhyloCSF{k}Regions.bed"), "rb").read() == gzip.open(os.path.join(R, f"{tag}.PhyloCSF{k}Regions.bed.gz"), "rb").read(), k
+
+
+@pytest.mark.parametrize("tag", ["smooth53", "smooth12"])
+def test_hmm_smoothing_matches_reference(golden_dir, tmp_path, tag):
+    """PhyloCSF-HMM stage alone (host/hmm.hpp; HMM parameter estimation from coding exons, scaled forward-backward, Viterbi
+    regions) on raw tracks written by the reference: smoothed wigs and region BEDs byte-identical to what the reference
+    itself wrote (tests/golden/make_ref_fixtures.py).  smooth12 has > 20 000 gaps: the std::shuffle subsampling path."""
+    _need_bin()
+    raw, exons, glen = _smooth_inputs(golden_dir, tmp_path, tag)
+    out = os.path.join(str(tmp_path), "out_" + tag)
+    subprocess.run([BIN, "smooth-tracks", "--genome-length", glen, "--coding-exons", exons, raw, out], check=True, capture_output=True)
+    _assert_smoothed(out, golden_dir, tag)
+
+
+@pytest.mark.gpu
+def test_build_tracks_cli_smoothing(golden_dir, tmp_path):
+    """build-tracks --output-phylo 1 --output-regions 1 --output-raw-phylo 0 end to end (CUDA likelihoods -> raw text -> HMM):
+    identical to the reference's files, raw tracks removed afterwards (build_tracks.hpp:343-346)."""
+    _need_bin()
+    G = os.path.join(golden_dir, "build-tracks")
+    maf = _gunzip(os.path.join(G, "galGal6_chr22_25_28_each_30k_bases.maf.gz"), str(tmp_path))
+    _, exons, glen = _smooth_inputs(golden_dir, tmp_path, "smooth53")
+    out = os.path.join(str(tmp_path), "out_s")
+    subprocess.run([BIN, "build-tracks", "--threads", "4", "--output-phylo", "1", "--output-regions", "1", "--output-raw-phylo", "0",
+                    "--genome-length", glen, "--coding-exons", exons, "--output", out, os.path.join(G, "53birds"), maf], check=True, capture_output=True)
+    _assert_smoothed(out, golden_dir, "smooth53")
+    assert not os.path.exists(os.path.join(out, "PhyloCSFRaw+1.wig")) and os.path.exists(os.path.join(out, "PhyloCSFpower.wig"))
+    r = subprocess.run([BIN, "build-tracks", "--output-phylo", "1", "--output", out, os.path.join(G, "53birds"), maf], capture_output=True, text=True)
+    assert r.returncode != 0 and "--genome-length and --coding-exons" in r.stdout
+
+
 @pytest.mark.gpu
 def test_build_tracks_cli_golden(golden_dir, tmp_path):
     """Config 1 through the command line tool: the reference's seven expected wig files, byte for byte (FP64 path), with

@@ -56,3 +56,26 @@ def pattern_index_reference(plus: np.ndarray, minus: np.ndarray, chunk_cols: int
             keys.append(minus[:, o].tobytes())
         out[2 * c0:2 * c1] = first_occurrence_ranks(keys)
     return out
+
+
+def write_synthetic_exons(path: str, n: int = 46000, seed: int = 99) -> None:
+    """A deterministic BED-like coding-exon list (chrom, strand, phase, start, end) with overlaps, for the HMM
+    parameter estimation (reference src/estimate_hmm_parameter.hpp:243-340): more than 2 x 20 000 inter-exon gaps in a
+    few chrom:strand:phase classes so that the gap subsampling (std::shuffle, default_random_engine(0)) is exercised."""
+    x = seed
+    pos = {}
+    with open(path, "w") as fh:
+        for _ in range(n):
+            x = (x * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
+            chrom = "chr%d" % (1 + (x >> 60) % 2)
+            strand = "+-"[(x >> 58) & 1]
+            phase = (x >> 55) % 3
+            key = (chrom, strand, phase)
+            gap_class = (x >> 40) % 10
+            gap = 30 + (x >> 20) % (200 if gap_class < 3 else 6000 if gap_class < 9 else 150000)
+            length = 20 + (x >> 8) % 400
+            start = pos.get(key, 1000) + gap - (120 if (x >> 5) % 17 == 0 else 0)      # now and then an overlap
+            start = max(1, start)
+            end = start + length
+            pos[key] = end
+            fh.write("%s\t%s\t%d\t%d\t%d\n" % (chrom, strand, phase, start, end))

@@ -170,6 +170,12 @@ def main():
                          "f64: FP64 DMMA path (parity anchor, byte-identical wig text); f32: split-TF32 mma.sync path")
     args = ap.parse_args()
 
+    # stdout carries exactly one JSON line: libraries that write to fd 1 (NCCL prints its version banner there at
+    # communicator creation) are sent to stderr instead
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -224,7 +230,7 @@ def main():
             "config": {"workload": workload, "sample_columns_per_step": S, "model": args.model},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": ncores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}))
+            "gpu_launches": 0}), file=json_out, flush=True)
         return
 
     import torch
@@ -402,7 +408,7 @@ def main():
                 out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": ncores, "kind": "port", "seconds": dt,
                                        "sample": f"first {S} columns of the step's batch, oracle port of the reference path, "
                                                  f"{ncores} processes"}
-        print(json.dumps(out), flush=True)
+        print(json.dumps(out), file=json_out, flush=True)
     dm.close()
     if world > 1:
         dist.destroy_process_group()

@@ -119,7 +119,7 @@ pcsf_status pcsf_set_timing(pcsf_model *m, int enabled);
 
 /* ---- score-msa path ---------------------------------------------------------------------------- */
 
-typedef enum { PCSF_STRATEGY_MLE = 0, PCSF_STRATEGY_FIXED = 1 } pcsf_strategy;
+typedef enum { PCSF_STRATEGY_MLE = 0, PCSF_STRATEGY_FIXED = 1, PCSF_STRATEGY_OMEGA = 2 } pcsf_strategy;
 
 /*
  * n_aln alignments, each scored on its own in frame +1 from offset 0 (score_msa.hpp:102-116).
@@ -129,6 +129,9 @@ typedef enum { PCSF_STRATEGY_MLE = 0, PCSF_STRATEGY_FIXED = 1 } pcsf_strategy;
  *   bls       [n_aln] float(compute_bls_score<false>)  or NULL (score_msa.hpp:132)
  * MLE replays mt19937(42) per alignment (score_msa.hpp:115) and GSL's Brent minimiser
  * (fixed_lik.hpp:469-544).
+ * OMEGA (run.hpp:59-182, omega.hpp): phylo = float(10*(lpr_H1 - lpr_H0)/ln 10) from the alternating rho / kappa fits of the
+ * two dN/dS hypotheses on a Q(kappa, omega, F3x4) built per alignment; there is no ancestral score for it (the reference
+ * returns NaN, run.hpp:181): anc, if given, is filled with NaN.
  */
 pcsf_status pcsf_score_msa(pcsf_model *m, pcsf_strategy strategy, int32_t n_aln, const uint8_t *seqs,
                            const int64_t *offset, const int64_t *len, float *phylo, float *anc, float *bls);

@@ -48,6 +48,9 @@ def lib():
         L.orc_max_lik.argtypes = [C.c_void_p, _u8p, C.c_int64, C.c_int64, C.c_int, C.c_double, C.c_double,
                                   C.c_double, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                   C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.orc_omega.restype = C.c_int
+        L.orc_omega.argtypes = [C.c_int, _i16p, _i16p, C.c_void_p, _u8p, C.c_int64, C.c_int64, C.c_uint32,
+                                C.POINTER(C.c_double), C.c_void_p]
         L.orc_mt_seed.argtypes = [C.c_void_p, C.c_uint32]
         L.orc_mt_next.restype = C.c_uint32
         L.orc_mt_next.argtypes = [C.c_void_p]
@@ -222,3 +225,17 @@ def run_mle(mc: OracleModel, mnc: OracleModel, peptides: np.ndarray, compute_anc
         return np.float32(np.nan), np.float32(np.nan), info
     ln10 = np.log(10.0)
     return np.float32(10.0 * (lc - lnc) / ln10), np.float32(10.0 * (ac - anc) / ln10), info
+
+
+def run_omega(tree, peptides: np.ndarray, seed: int = 42):
+    """run.hpp:59-182 OMEGA: (float32 score, info dict); NaN if the reference would have thrown."""
+    pep = np.ascontiguousarray(peptides, np.uint8)
+    nl, K = pep.shape
+    c1 = np.ascontiguousarray(tree.child1, np.int16)
+    c2 = np.ascontiguousarray(tree.child2, np.int16)
+    bl = np.ascontiguousarray(tree.branch_len, np.float32)
+    score = C.c_double()
+    info = np.zeros(5)
+    st = lib().orc_omega(nl, c1, c2, bl.ctypes.data, pep, K, K, seed, C.byref(score), info.ctypes.data)
+    d = dict(rho=info[0], kappa=info[1], lpr_h0=info[2], lpr_h1=info[3], evals=int(info[4]), status=st)
+    return (np.float32(np.nan) if st else np.float32(score.value)), d

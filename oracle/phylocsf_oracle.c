@@ -23,6 +23,9 @@
 #include <string.h>
 
 #define NS 64 /* codon states */
+#ifndef M_PI
+#define M_PI 3.14159265358979323846 /* -std=c11 hides it */
+#endif
 
 /* ------------------------------------------------------------------------------------------------
  * translation.hpp:29-53 get_dna_id — ACGT/acgt -> 0..3, ".-Nn" -> 4, anything else -> 99 (the
@@ -398,6 +401,16 @@ double orc_uniform(orc_mt19937 *g, double width) {
     return ret * width + 0.0;
 }
 
+/* OMEGA strategy state (run.hpp:59-182): q_settings = kappa, omega, sigma, 9 F3x4 ratios; tree_settings = rho. */
+typedef struct {
+    double qs[12];
+    double rho;
+} orc_omega_state;
+
+static int omega_set_q(orc_model *m, const double *qs);
+static double omega_lpr_rho(double rho);
+static double omega_lpr_kappa(double kappa);
+
 typedef struct {
     orc_model *m;
     const uint8_t *peptides;
@@ -406,25 +419,48 @@ typedef struct {
     double x, lpr, elpr_anc;
     int status;  /* first PhyloModel_make error (the reference throws std::runtime_error) */
     int evals;
+    int kind;    /* 0: lpr_leaves(rho) of a fixed Q (MLE); 1: OMEGA rho fit; 2: OMEGA kappa fit */
+    orc_omega_state *om;
 } orc_fit;
 
-/* fixed_lik.hpp:460-467 minimizer_lpr_leaves: returns -lpr, records x/lpr/elpr_anc. */
+/* fixed_lik.hpp:460-467 minimizer_lpr_leaves (kind 0): returns -lpr, records x/lpr/elpr_anc.
+ * omega.hpp:205-233 minimizer_lpr_leaves_rho / _kappa (kinds 1, 2): the same with the half-Cauchy / Gamma log-prior
+ * added; the kappa variant rebuilds Q and its eigensystem first and keeps the last evaluated rho. */
 static double fit_eval(orc_fit *p, double x) {
     p->x = x;
     p->evals++;
-    int rc = orc_model_set_rho(p->m, x);
+    int rc;
+    if (p->kind == 2) {
+        p->om->qs[0] = x;
+        omega_set_q(p->m, p->om->qs);
+        rc = orc_model_set_rho(p->m, p->om->rho);
+    } else {
+        if (p->kind == 1) p->om->rho = x;
+        rc = orc_model_set_rho(p->m, x);
+    }
     if (rc && !p->status) p->status = rc;
     orc_lpr_leaves(p->m, p->peptides, p->K, p->stride, p->compute_anc, &p->lpr, &p->elpr_anc, NULL, NULL);
+    if (p->kind == 1) p->lpr += omega_lpr_rho(x);
+    if (p->kind == 2) p->lpr += omega_lpr_kappa(x);
     return -p->lpr;
 }
 
 /* fixed_lik.hpp:469-544 fit_find_init + max_lik_lpr_leaves with gsl_min_fminimizer_brent restated
  * (GSL 2.x min/brent.c + min/fsolver.c).  Returns 0 or the first P-matrix error.
  * On error the reference would have thrown at that evaluation; the caller maps that to NaN. */
+static int max_lik_core(orc_fit *pp_, double init, double lo, double hi, orc_mt19937 *gen, double *lpr, double *elpr_anc,
+                        double *x_final, int *n_evals);
+
 int orc_max_lik(orc_model *m, const uint8_t *peptides, int64_t K, int64_t stride, int compute_anc,
                 double init, double lo, double hi, orc_mt19937 *gen, double *lpr, double *elpr_anc,
                 double *x_final, int *n_evals) {
-    orc_fit p = {m, peptides, K, stride, compute_anc, 0.0, 0.0, 0.0, 0, 0};
+    orc_fit p = {m, peptides, K, stride, compute_anc, 0.0, 0.0, 0.0, 0, 0, 0, NULL};
+    return max_lik_core(&p, init, lo, hi, gen, lpr, elpr_anc, x_final, n_evals);
+}
+
+static int max_lik_core(orc_fit *pp_, double init, double lo, double hi, orc_mt19937 *gen, double *lpr, double *elpr_anc,
+                        double *x_final, int *n_evals) {
+#define p (*pp_)
     const double width = log(hi) - log(lo);
     const double flo = -fit_eval(&p, lo);
     const double fhi = -fit_eval(&p, hi);
@@ -506,6 +542,137 @@ done:
     if (x_final) *x_final = p.x;
     if (n_evals) *n_evals = p.evals;
     return p.status;
+#undef p
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * OMEGA strategy (score-msa --strategy omega): run.hpp:59-182 + omega.hpp.
+ * translation.hpp: the standard genetic code indexed by 16a+4b+c over A,C,G,T. */
+static char omega_aa(int codon) {
+    static const char tcag[] = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
+    static const int to_tcag[4] = {2, 1, 3, 0}; /* A C G T -> position in T C A G */
+    return tcag[16 * to_tcag[codon / 16] + 4 * to_tcag[(codon / 4) % 4] + to_tcag[codon % 4]];
+}
+
+/* omega.hpp:8-19 pi_expr_sc */
+static double omega_pi_sc(const double *qs, int codon) {
+    const int i1 = codon / 16, i2 = (codon - 16 * i1) / 4, i3 = codon - 16 * i1 - 4 * i2;
+    const double f1 = ((i1 == 3) ? 1.0 : qs[3 + i1]) / (1.0 + qs[3] + qs[4] + qs[5]);
+    const double f2 = ((i2 == 3) ? 1.0 : qs[6 + i2]) / (1.0 + qs[6] + qs[7] + qs[8]);
+    const double f3 = ((i3 == 3) ? 1.0 : qs[9 + i3]) / (1.0 + qs[9] + qs[10] + qs[11]);
+    return f1 * f2 * f3;
+}
+
+/* omega.hpp:21-36 pi_expr + :38-95 comp_q_p14n + :97-128 scale; then instantiate_qs (instance.hpp:309-434) and the
+ * equilibrium prior (fixed_lik.hpp:323-346).  pi is a positive multiple of the stationary distribution, which is all the
+ * symmetrisation in orc_eigen needs. */
+static int omega_set_q(orc_model *m, const double *qs) {
+    double pi[NS];
+    double *Q = (double *)malloc(sizeof(double) * NS * NS);
+    const double kappa = qs[0], omega = qs[1], sigma = qs[2];
+    const double denom = 1.0 - ((1.0 - sigma) * (omega_pi_sc(qs, 3 * 16 + 0 * 4 + 0) + omega_pi_sc(qs, 3 * 16 + 0 * 4 + 2) +
+                                                 omega_pi_sc(qs, 3 * 16 + 2 * 4 + 0)));
+    for (int i = 0; i < NS; ++i) pi[i] = omega_pi_sc(qs, i) / denom;
+    for (int i = 0; i < NS; ++i) {
+        const int i1 = i / 16, i2 = (i / 4) % 4, i3 = i % 4;
+        const char iaa = omega_aa(i);
+        for (int j = 0; j < NS; ++j) {
+            const int j1 = j / 16, j2 = (j / 4) % 4, j3 = j % 4;
+            double val = 0.0;
+            if ((i1 != j1) + (i2 != j2) + (i3 != j3) == 1) {
+                int transition = 0;
+                if (i1 != j1 && (i1 + j1 == 2 || i1 + j1 == 4)) transition = 1;
+                if (i2 != j2 && (i2 + j2 == 2 || i2 + j2 == 4)) transition = 1;
+                if (i3 != j3 && (i3 + j3 == 2 || i3 + j3 == 4)) transition = 1;
+                val = transition ? kappa : 1.0;
+                const char jaa = omega_aa(j);
+                val *= (iaa != '*' && jaa != '*' && iaa != jaa) ? omega : 1.0;
+                val *= pi[j];
+            }
+            Q[i * NS + j] = val;
+        }
+    }
+    for (int i = 0; i < NS; ++i) {
+        double val = 0.0;
+        for (int j = 0; j < NS; ++j)
+            if (i != j) val -= Q[i * NS + j];
+        Q[i * NS + i] = val;
+    }
+    double factor = 0.0;
+    for (int i = 0; i < NS; ++i) factor -= pi[i] * Q[i * NS + i];
+    for (int i = 0; i < NS * NS; ++i) Q[i] = Q[i] / factor;
+    orc_eigen(Q, pi, m->lambda, m->SR, m->SRinv);
+    orc_prior(m->lambda, m->SRinv, m->pi);
+    free(Q);
+    return 0;
+}
+
+/* omega.hpp:130-141 get_lpr_rho: half-Cauchy(mode 1, scale 0.5) log-density */
+static double omega_lpr_rho(double rho) {
+    const double mode = 1.0, scale = 0.5;
+    const double numer = 1.0 / (M_PI * scale * (1.0 + pow(((rho - mode) / scale), 2.0)));
+    const double cauchy_cdf = atan((0.0 - mode) / scale) / M_PI + 0.5;
+    const double denom = 1.0 - cauchy_cdf;
+    return log(numer) - log(denom);
+}
+
+/* omega.hpp:143-149 get_lpr_kappa: log Gamma(shape 7, scale 0.25) density at kappa - 1 + DBL_EPSILON
+ * (gsl_ran_gamma_pdf: exp((a-1) log(x/b) - x/b - lgamma(a)) / b) */
+static double omega_lpr_kappa(double kappa) {
+    const double k = kappa - 1.0 + 2.2204460492503131e-16;
+    const double a = 7.0, b = 0.25;
+    double g;
+    if (k < 0) g = 0;
+    else if (k == 0) g = 0;
+    else g = exp((a - 1) * log(k / b) - k / b - lgamma(a)) / b;
+    return log(g);
+}
+
+/* run.hpp:59-182, the OMEGA branch of run().  peptides: nl x K codon ids of frame +1 from offset 0.
+ * Returns 0 or the first PhyloModel_make error (the reference throws -> NaN row); *score = 10 (lpr_H1 - lpr_H0) / ln 10
+ * narrowed to float by the caller.  info (may be NULL): [0] rho, [1] kappa at the end, [2] lpr_H0, [3] lpr_H1, [4] evaluations.
+ * Not restated: the very first PhyloModel_make on the uniform-frequency Q (run.hpp:94-103), whose only observable effect is
+ * a throw when GSL's nonsymmetric solver returns a bad basis for that highly degenerate matrix. */
+int orc_omega(int nl, const int16_t *child1, const int16_t *child2, const float *bl, const uint8_t *peptides, int64_t K,
+              int64_t stride, uint32_t seed, double *score, double *info) {
+    orc_model *m = (orc_model *)calloc(1, sizeof(orc_model));
+    m->nl = nl; m->n = 2 * nl - 1; m->child1 = child1; m->child2 = child2; m->bl = bl;
+    m->P = (double *)malloc(sizeof(double) * (size_t)(m->n - 1) * NS * NS);
+    orc_omega_state om;
+    om.qs[0] = 2.5; om.qs[1] = 1.0; om.qs[2] = 1.0;
+    om.rho = 1.0;
+    /* update_f3x4 (run.hpp:106-134): pseudo-count 1, certain codons only */
+    double counts[3][4];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 4; ++j) counts[i][j] = 1.0;
+    for (int sp = 0; sp < nl; ++sp)
+        for (int64_t k = 0; k < K; ++k) {
+            const uint8_t c = peptides[(int64_t)sp * stride + k];
+            if (c != 64) { counts[0][c / 16] += 1; counts[1][(c / 4) % 4] += 1; counts[2][c % 4] += 1; }
+        }
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) om.qs[3 + 3 * i + j] = counts[i][j] / counts[i][3];
+    orc_mt19937 gen;
+    orc_mt_seed(&gen, seed);
+    int status = 0, evals = 0;
+    double lpr[2] = {0.0, 0.0}, anc = 0.0;
+    for (int h = 0; h < 2 && !status; ++h) {
+        if (h == 1) { om.qs[1] = 0.2; om.qs[2] = 0.01; }
+        omega_set_q(m, om.qs);
+        status = orc_model_set_rho(m, om.rho);          /* PhyloModel_make(inst, NULL, true) at run.hpp:139 / :167 */
+        for (int r = 0; r < 3 && !status; ++r) {
+            orc_fit p = {m, peptides, K, stride, 0, 0.0, 0.0, 0.0, 0, 0, 1, &om};
+            status = max_lik_core(&p, om.rho, 0.001, 10.0, &gen, &lpr[h], &anc, NULL, NULL);
+            evals += p.evals;
+            if (status) break;
+            orc_fit pk = {m, peptides, K, stride, 0, 0.0, 0.0, 0.0, 0, 0, 2, &om};
+            status = max_lik_core(&pk, om.qs[0], 1.0, 10.0, &gen, &lpr[h], &anc, NULL, NULL);
+            evals += pk.evals;
+        }
+    }
+    *score = 10.0 * (lpr[1] - lpr[0]) / log(10.0);
+    if (info) { info[0] = om.rho; info[1] = om.qs[0]; info[2] = lpr[0]; info[3] = lpr[1]; info[4] = (double)evals; }
+    free(m->P);
+    free(m);
+    return status;
 }
 
 /* ------------------------------------------------------------------------------------------------

@@ -29,6 +29,7 @@ TRACKS_TC5 = 0x10
 
 STRATEGY_MLE = 0
 STRATEGY_FIXED = 1
+STRATEGY_OMEGA = 2
 
 EXPORTS = [
     "pcsf_model_create", "pcsf_model_destroy", "pcsf_last_error", "pcsf_abi_version", "pcsf_tracks",

@@ -321,6 +321,7 @@ struct TileDesc {
     int32_t count;           // windows in this tile (<= 8 * nwarp)
     uint32_t win0;           // first window (index into ws.win_off) == output index
     uint32_t pad;
+    const double *pi;        // nullable: this tile's own root prior (OMEGA: the equilibrium of the slot's current Q)
 };
 
 struct PruneArgs {
@@ -497,7 +498,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) k_prune(const PruneArgs a) {
                         R[2 * nt] *= v.x; R[2 * nt + 1] *= v.y;
                     }
                 } else {  // OP_END: z = pi . alpha_root; log z; optional ancestral term
-                    const double *pi = s_pi + m * 128, *lpi = pi + 64;
+                    const double *pi = (PER_TILE && td.pi != nullptr) ? td.pi : s_pi + m * 128, *lpi = s_pi + m * 128 + 64;
                     double z = 0.0;
 #pragma unroll
                     for (int nt = 0; nt < 8; ++nt) {

@@ -117,6 +117,50 @@ __device__ inline void brent_update(MleSlot &s, double u, double fu) {
 
 enum : int32_t { PH_LO = 0, PH_HI, PH_TRY, PH_REEVAL, PH_SET_LO, PH_SET_HI, PH_SET_Z, PH_INIT_V, PH_ITER };
 
+// One step of max_lik_lpr_leaves (fixed_lik.hpp:469-544): s.lpr holds the value of the evaluation at s.x that was just
+// consumed; sets the next s.x and returns false, or returns true when the fit has ended (s.lpr = the LAST evaluation).
+__device__ inline bool fit_advance(MleSlot &s, double lo, double hi, double init, const double *__restrict__ cand) {
+    const double F = -s.lpr;   // minimizer_lpr_leaves returns -lpr (fixed_lik.hpp:466)
+    switch (s.phase) {
+    case PH_LO: s.flo = s.lpr; s.x = hi; s.phase = PH_HI; break;
+    case PH_HI: s.fhi = s.lpr; s.x = init; s.tries = 0; s.phase = PH_TRY; break;
+    case PH_TRY:
+        s.fx = s.lpr;
+        if (s.tries < MLE_MAX_TRIES && (s.fx <= s.flo || s.fx <= s.fhi)) {
+            s.x = cand[s.rng_pos++];
+            ++s.tries;
+        } else {
+            s.xsel = (s.tries == MLE_MAX_TRIES) ? (s.flo > s.fhi ? lo : hi) : s.x;
+            s.x = s.xsel;
+            s.phase = PH_REEVAL;
+        }
+        break;
+    case PH_REEVAL:
+        if (lo < s.xsel && s.xsel < hi) { s.x = lo; s.phase = PH_SET_LO; }
+        else return true;
+        break;
+    case PH_SET_LO: s.x = hi; s.phase = PH_SET_HI; break;
+    case PH_SET_HI: s.x = s.xsel; s.phase = PH_SET_Z; break;
+    case PH_SET_Z:
+        s.z = s.xsel; s.fz = F; s.xl = lo; s.xu = hi;
+        s.v = lo + 0.3819660 * (hi - lo); s.w = s.v; s.d = 0.0; s.e = 0.0;
+        s.x = s.v; s.phase = PH_INIT_V;
+        break;
+    case PH_INIT_V:
+        s.fv = F; s.fw = F;
+        s.iter = 250;
+        s.x = brent_next_u(s);
+        s.phase = PH_ITER;
+        break;
+    case PH_ITER:
+        brent_update(s, s.x, F);
+        if (((s.xu - s.xl) / s.z) <= 0.01 || --s.iter <= 0) return true;   // fixed_lik.hpp:533-536
+        s.x = brent_next_u(s);
+        break;
+    }
+    return false;
+}
+
 // One thread per slot.  cand[i] = exp(log(lo) + U_i) (host-tabulated).  queue_head: next alignment to fit.
 // Uses __dadd_rn etc. only where the reference's order matters (sequential sums); contraction elsewhere is
 // harmless (the iterate sequence is compared at 1e-3 decibans / the reference's own CI tolerance).
@@ -162,44 +206,7 @@ __global__ void k_mle_step(MleSlot *slots, int n_slots, int n_aln, int *queue_he
         if (s.failed) {
             model_done = true;
         } else {
-            const double F = -s.lpr;   // minimizer_lpr_leaves returns -lpr (fixed_lik.hpp:466)
-            switch (s.phase) {
-            case PH_LO: s.flo = s.lpr; s.x = hi; s.phase = PH_HI; break;
-            case PH_HI: s.fhi = s.lpr; s.x = init; s.tries = 0; s.phase = PH_TRY; break;
-            case PH_TRY:
-                s.fx = s.lpr;
-                if (s.tries < MLE_MAX_TRIES && (s.fx <= s.flo || s.fx <= s.fhi)) {
-                    s.x = cand[s.rng_pos++];
-                    ++s.tries;
-                } else {
-                    s.xsel = (s.tries == MLE_MAX_TRIES) ? (s.flo > s.fhi ? lo : hi) : s.x;
-                    s.x = s.xsel;
-                    s.phase = PH_REEVAL;
-                }
-                break;
-            case PH_REEVAL:
-                if (lo < s.xsel && s.xsel < hi) { s.x = lo; s.phase = PH_SET_LO; }
-                else model_done = true;
-                break;
-            case PH_SET_LO: s.x = hi; s.phase = PH_SET_HI; break;
-            case PH_SET_HI: s.x = s.xsel; s.phase = PH_SET_Z; break;
-            case PH_SET_Z:
-                s.z = s.xsel; s.fz = F; s.xl = lo; s.xu = hi;
-                s.v = lo + 0.3819660 * (hi - lo); s.w = s.v; s.d = 0.0; s.e = 0.0;
-                s.x = s.v; s.phase = PH_INIT_V;
-                break;
-            case PH_INIT_V:
-                s.fv = F; s.fw = F;
-                s.iter = 250;
-                s.x = brent_next_u(s);
-                s.phase = PH_ITER;
-                break;
-            case PH_ITER:
-                brent_update(s, s.x, F);
-                if (((s.xu - s.xl) / s.z) <= 0.01 || --s.iter <= 0) model_done = true;   // fixed_lik.hpp:533-536
-                else s.x = brent_next_u(s);
-                break;
-            }
+            model_done = fit_advance(s, lo, hi, init, cand);
         }
         if (!model_done) { s.pending = 1; break; }
         // max_lik_lpr_leaves returns the LAST evaluation's lpr / elpr_anc (fixed_lik.hpp:542-543)
@@ -225,7 +232,8 @@ __global__ void k_mle_step(MleSlot *slots, int n_slots, int n_aln, int *queue_he
 // Single block: tile descriptors for every slot with a pending evaluation.
 __global__ void __launch_bounds__(1024) k_mle_plan(const MleSlot *__restrict__ slots, int n_slots, const double *pbase,
                                                     size_t slot_stride /* doubles */, size_t leaf_off /* doubles */, int tw /* windows per tile */,
-                                                    TileDesc *__restrict__ tiles, uint32_t *__restrict__ n_tiles) {
+                                                    TileDesc *__restrict__ tiles, uint32_t *__restrict__ n_tiles,
+                                                    const double *pi_slots = nullptr /* [slot][64], OMEGA */) {
     __shared__ uint32_t sh[33];
     const uint32_t per = (n_slots + 1023) / 1024;
     const uint32_t base = threadIdx.x * per;
@@ -249,6 +257,7 @@ __global__ void __launch_bounds__(1024) k_mle_plan(const MleSlot *__restrict__ s
             { const int64_t rem = s.K - tw * (int64_t)t; d.count = (int32_t)(rem < tw ? rem : tw); }
             d.win0 = (uint32_t)(s.win0 + tw * (int64_t)t);
             d.pad = 0;
+            d.pi = pi_slots ? pi_slots + (size_t)si * 64 : nullptr;
             tiles[run + t] = d;
         }
         run += nt;
@@ -264,16 +273,18 @@ constexpr int EX_BSTRIDE = 68;   // padded row stride of the shared B operand (c
 __global__ void __launch_bounds__(128) k_mle_expm(const MleSlot *__restrict__ slots, int n_branches, int nl,
                                                   const float *__restrict__ bl, const double *__restrict__ eig0,
                                                   const double *__restrict__ eig1, const int32_t *__restrict__ edge_to_gemm,
-                                                  double *pbase, size_t slot_stride, size_t leaf_off, int *__restrict__ expm_err) {
+                                                  double *pbase, size_t slot_stride, size_t leaf_off, int *__restrict__ expm_err,
+                                                  const double *__restrict__ eig_slots = nullptr /* OMEGA: [slot][64 + 2*4096] */,
+                                                  const double *__restrict__ rho_slots = nullptr /* OMEGA: tree scale per slot */) {
     __shared__ double sB[64 * EX_BSTRIDE];
     __shared__ double sEx[64];
     const int si = blockIdx.x / n_branches, b = blockIdx.x % n_branches;
     const MleSlot &s = slots[si];
     if (s.aln < 0 || !s.pending) return;
-    const double *eig = s.model == 0 ? eig0 : eig1;
+    const double *eig = eig_slots ? eig_slots + (size_t)si * (64 + 2 * 4096) : (s.model == 0 ? eig0 : eig1);
     const double *lambda = eig, *SR = eig + 64, *SRinv = eig + 64 + 4096;
     // instantiate_tree: float(double(bl) * rho), read back as double (instance.hpp:299-307, :497)
-    const double t = (double)(float)((double)bl[b] * s.x);
+    const double t = (double)(float)((double)bl[b] * (rho_slots ? rho_slots[si] : s.x));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
     if (tid < 64) sEx[tid] = exp(lambda[tid] * t);
     __syncthreads();

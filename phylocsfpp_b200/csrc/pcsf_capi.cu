@@ -17,6 +17,7 @@
 
 #include "kernels.cuh"
 #include "mle.cuh"
+#include "omega.cuh"
 #include "prune_f32.cuh"
 #include "prune_tc5.cuh"
 
@@ -509,7 +510,7 @@ extern "C" pcsf_status pcsf_score_msa(pcsf_model *m, pcsf_strategy strategy, int
                                       const int64_t *offset, const int64_t *len, float *phylo, float *anc, float *bls) {
     if (!m || n_aln < 0 || (n_aln > 0 && (!seqs || !offset || !len)))
         return fail(PCSF_ERR_INVALID, "pcsf_score_msa: bad argument");
-    if (strategy != PCSF_STRATEGY_FIXED && strategy != PCSF_STRATEGY_MLE)
+    if (strategy != PCSF_STRATEGY_FIXED && strategy != PCSF_STRATEGY_MLE && strategy != PCSF_STRATEGY_OMEGA)
         return fail(PCSF_ERR_INVALID, "pcsf_score_msa: unknown strategy");
     CK(cudaSetDevice(m->device));
     if (n_aln == 0) return PCSF_OK;
@@ -570,6 +571,25 @@ extern "C" pcsf_status pcsf_score_msa(pcsf_model *m, pcsf_strategy strategy, int
                                                        nwin, d_blraw, m->host.bls_all, phylo ? d_phylo : nullptr,
                                                        anc ? d_anc : nullptr, bls ? d_bls : nullptr);
         CK(cudaGetLastError());
+    } else if (strategy == PCSF_STRATEGY_OMEGA) {
+        OmegaBatch b{};
+        b.n_aln = n_aln;
+        b.d_win_start = reinterpret_cast<const int64_t *>(mb + o_ws);
+        b.d_len = reinterpret_cast<const int64_t *>(mb + o_len);
+        b.ws = ws;
+        b.nwin = nwin;
+        b.d_phylo = phylo ? d_phylo : nullptr;
+        if ((rc = omega_run(m->host, b, m->d_bl, m->d_program, m->d_pi, m->d_logpi, m->mle, m->sm_count, m->prune_smem, m->prune_nwarp, st,
+                            g_err, &m->launches)))
+            return rc;
+        if (bls) {
+            CK(m->perwin.reserve(64));
+            k_aln_sums<<<(n_aln + 127) / 128, 128, 0, st>>>(n_aln, reinterpret_cast<const int64_t *>(mb + o_ws),
+                                                           reinterpret_cast<const int64_t *>(mb + o_cs),
+                                                           reinterpret_cast<const int64_t *>(mb + o_len), m->perwin.as<double>(),
+                                                           0, d_blraw, m->host.bls_all, nullptr, nullptr, d_bls);
+            CK(cudaGetLastError());
+        }
     } else {
         MleBatch b{};
         b.n_aln = n_aln;
@@ -599,7 +619,8 @@ extern "C" pcsf_status pcsf_score_msa(pcsf_model *m, pcsf_strategy strategy, int
     CK(cudaMemcpy(&bad, m->d_bad, sizeof(int), cudaMemcpyDeviceToHost));
     if (bad) return fail(PCSF_ERR_BAD_CHAR, "alignment contains a character outside ACGTacgt.-Nn (reference: exit(37))");
     if (phylo) CK(cudaMemcpy(phylo, d_phylo, (size_t)n_aln * 4, cudaMemcpyDeviceToHost));
-    if (anc) CK(cudaMemcpy(anc, d_anc, (size_t)n_aln * 4, cudaMemcpyDeviceToHost));
+    if (anc && strategy == PCSF_STRATEGY_OMEGA) { for (int i = 0; i < n_aln; ++i) anc[i] = nanf(""); }
+    else if (anc) CK(cudaMemcpy(anc, d_anc, (size_t)n_aln * 4, cudaMemcpyDeviceToHost));
     if (bls) CK(cudaMemcpy(bls, d_bls, (size_t)n_aln * 4, cudaMemcpyDeviceToHost));
     return PCSF_OK;
 }

@@ -10,7 +10,7 @@
 // output does not depend on the thread or GPU count (the reference merges its per-job files in job order,
 // build_tracks.hpp:27-53,245-259).
 // --output-phylo / --output-regions: the PhyloCSF-HMM smoothing of the raw tracks stays on the host (hmm.hpp).
-// Not in this tool: the OMEGA and FIXED_MEAN strategies.
+// Not in this tool: the FIXED_MEAN strategy (score-msa --strategy fixed_mean).
 #include <cinttypes>
 #include <chrono>
 #include <condition_variable>
@@ -348,8 +348,13 @@ int main_score_msa(int argc, char **argv) {
     pcsf_strategy strategy;
     if (strat == "mle") strategy = PCSF_STRATEGY_MLE;
     else if (strat == "fixed") strategy = PCSF_STRATEGY_FIXED;
-    else die("--strategy %s is not part of this tool (MLE and FIXED are)", strat.c_str());
+    else if (strat == "omega") strategy = PCSF_STRATEGY_OMEGA;
+    else die("--strategy %s is not part of this tool (MLE, FIXED and OMEGA are)", strat.c_str());
     const bool comp_phylo = a.boolean("comp-phylo", true), comp_anc = a.boolean("comp-anc", false), comp_bls = true;   // no --comp-bls in the reference
+    if (strategy == PCSF_STRATEGY_OMEGA && comp_anc) {          // score_msa.hpp:338-342
+        printf("\033[31mThe ancestral sequence composition cannot be computed in the Omega mode!\n\033[0m");
+        return -1;
+    }
     const int threads = std::max(1, a.integer("threads", (int)std::thread::hardware_concurrency()));
     const int gpus = std::max(1, a.integer("gpus", 1));
     const int workers_n = std::min(threads, 2 * gpus);      // the per-call batch is the unit of GPU work; parsing runs inside the workers
@@ -516,7 +521,7 @@ int main(int argc, char **argv) {
                "  phylocsf_b200 build-tracks [--output-raw-phylo BOOL] [--output-phylo BOOL] [--output-regions BOOL] [--genome-length INT]\n"
                "                             [--coding-exons FILE] [--power-threshold FLOAT] [--threads INT] [--gpus INT]\n"
                "                             [--precision f64|tc5|f32] [--output DIR] [--mapping FILE] [--species LIST] <model> <maf>...\n"
-               "  phylocsf_b200 score-msa    [--strategy MLE|FIXED] [--comp-phylo BOOL] [--comp-anc BOOL] [--threads INT] [--gpus INT]\n"
+               "  phylocsf_b200 score-msa    [--strategy MLE|FIXED|OMEGA] [--comp-phylo BOOL] [--comp-anc BOOL] [--threads INT] [--gpus INT]\n"
                "                             [--output DIR] [--mapping FILE] [--species LIST] <model> <maf>...\n");
         return argc < 2 ? 1 : 0;
     }

@@ -96,3 +96,21 @@ def test_mle_vs_oracle_random():
         tight += abs(float(p) - float(rp)) <= 1e-3 and abs(float(an) - float(ra)) <= 1e-3
     assert tight >= len(alns) - 1
     dm.close()
+
+
+def test_omega_vs_oracle_random():
+    """pcsf_score_msa(OMEGA) against the oracle's restatement of run.hpp:59-182 on random alignments, incl. L < 3 (prior-only
+    fits: both hypotheses see the same function, score 0) — the same 1 %-bracket tolerance as against the reference."""
+    model = load_model("12flies")
+    dm = capi.DeviceModel(model)
+    alns = [random_alignment(model.nl, L, seed=300 + L, gap=0.2) for L in (2, 30, 61, 150, 333)]
+    phylo, anc, bls = dm.score_msa(alns, capi.STRATEGY_OMEGA, comp_anc=False)
+    d = []
+    for a, p, b in zip(alns, phylo, bls):
+        s, info = orc.run_omega(model.tree, orc.translate(a))
+        print(a.shape[1], float(p), float(s), info["evals"])
+        d.append(abs(float(p) - float(s)))
+        assert np.float32(orc.bls(model.tree, a, per_base=False)[0]) == b
+    assert max(d) ** 2 <= 0.1 and min(d) <= 1e-3
+    assert abs(float(phylo[0])) < 1e-6
+    dm.close()

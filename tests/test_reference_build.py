@@ -130,6 +130,24 @@ def test_oracle_vs_reference_msa29(golden_dir):
     assert tight >= len(picks) - 1
 
 
+def test_oracle_omega_vs_reference_msa29(golden_dir):
+    """OMEGA restatement (orc_omega) against the reference's own output: the reference's CI tolerance for this strategy is
+    a squared error of 0.1 (test/tests.sh:46) because the result is the LAST Brent evaluation of a 1 %-bracket search."""
+    R = os.path.join(golden_dir, "ref-generated")
+    m = load_model("29mammals", SPECIES29)
+    alns = list(MafReader(os.path.join(R, "msa29.maf.gz"), m.seqid_to_phyloid, m.nl, False, warn=False))
+    gold = _rows(os.path.join(R, "msa29.omega.scores"))
+    assert len(alns) == len(gold)
+    close = 0
+    picks = [0, 2, 5, 7, 10, 12]
+    for i in picks:
+        s, info = orc.run_omega(m.tree, orc.translate(alns[i].seqs))
+        assert info["status"] == 0 and 150 <= info["evals"] <= 12 * 260
+        assert (float(s) - float(gold[i][4])) ** 2 <= 0.1, (i, s, gold[i])
+        close += abs(float(s) - float(gold[i][4])) <= 0.01
+    assert close >= 2
+
+
 # ------------------------------------------------------------------------------------------------ 3. product vs reference
 @pytest.mark.gpu
 def test_cli_build_tracks_vs_reference_tracks12(golden_dir, tmp_path):
@@ -171,3 +189,23 @@ def test_cli_score_msa_vs_reference_msa29(golden_dir, tmp_path, strategy):
             assert d ** 2 <= 0.001          # the reference's own CI tolerance (test/tests.sh:41)
             loose += d > 1e-3               # a Brent trajectory that forks on ~1e-13 differences in P(t)
     assert loose <= max(1, len(gold) // 25)
+
+
+@pytest.mark.gpu
+def test_cli_score_msa_omega_vs_reference_msa29(golden_dir, tmp_path):
+    """score-msa --strategy omega (batched Jacobi eigensolver + twelve Brent fits per alignment on the GPU) against the
+    reference's own output, at the reference's CI tolerance for this strategy (squared error <= 0.1, test/tests.sh:46)."""
+    R = os.path.join(golden_dir, "ref-generated")
+    maf = _gunzip(os.path.join(R, "msa29.maf.gz"), os.path.join(str(tmp_path), "msa29.maf"))
+    out = os.path.join(str(tmp_path), "o")
+    subprocess.run([BIN, "score-msa", "--strategy", "omega", "--species", SPECIES29, "--output", out, "29mammals", maf], check=True, capture_output=True)
+    ours, gold = _rows(os.path.join(out, "msa29.maf.scores")), _rows(os.path.join(R, "msa29.omega.scores"))
+    assert len(ours) == len(gold)
+    d = []
+    for o, g in zip(ours, gold):
+        assert o[:4] == g[:4] and o[5] == g[5] and len(o) == 6
+        d.append(abs(float(o[4]) - float(g[4])))
+    print("omega |d| vs reference: max %.3g, median %.3g, <=1e-2: %d of %d" % (max(d), sorted(d)[len(d) // 2], sum(x <= 1e-2 for x in d), len(d)))
+    assert max(d) ** 2 <= 0.1
+    r = subprocess.run([BIN, "score-msa", "--strategy", "omega", "--comp-anc", "1", "29mammals", maf], capture_output=True, text=True)
+    assert r.returncode != 0 and "Omega mode" in r.stdout

@@ -20,6 +20,7 @@
 #include "omega.cuh"
 #include "prune_f32.cuh"
 #include "prune_tc5.cuh"
+#include "prune_tc5h.cuh"
 
 using namespace pcsf;
 
@@ -64,6 +65,9 @@ struct pcsf_model {
     float *d_tc5_scratch = nullptr;      // stack spill of k_prune_tc5: [sm_count][2][max_stack][T5_STACK_ENTRY_FLOATS]
     size_t prune_tc5_smem = 0;
     int tc5_nstage = 2, tc5_nlstage = 3;
+    size_t prune_tc5h_smem = 0;          // k_prune_tc5h (16 epilogue warps): experimental, PCSF_TC5_VARIANT=half selects it (slower: see DESIGN.md)
+    int tc5h_nstage = 2, tc5h_nlstage = 3;
+    bool tc5_half = false;
     int32_t *d_program = nullptr;
     BlsNode *d_bls_prog = nullptr;
     float *d_bl = nullptr;
@@ -149,6 +153,12 @@ extern "C" pcsf_status pcsf_model_create(const pcsf_model_desc *d, int device, p
     if (const char *e = getenv("PCSF_TC5_NLSTAGE")) m->tc5_nlstage = std::max(3, std::min(m->tc5_nlstage, atoi(e)));
     m->prune_tc5_smem = prune_tc5_smem_bytes(m->host.nl, (int)m->host.tc5_steps.size(), m->tc5_nstage, m->tc5_nlstage);
     CK(cudaFuncSetAttribute(k_prune_tc5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->prune_tc5_smem));
+    prune_tc5h_pick_stages(m->host.nl, (int)m->host.tc5_steps.size(), &m->tc5h_nstage, &m->tc5h_nlstage);
+    if (const char *e = getenv("PCSF_TC5_NSTAGE")) m->tc5h_nstage = std::max(2, std::min(m->tc5h_nstage, atoi(e)));
+    if (const char *e = getenv("PCSF_TC5_NLSTAGE")) m->tc5h_nlstage = std::max(3, std::min(m->tc5h_nlstage, atoi(e)));
+    m->prune_tc5h_smem = prune_tc5h_smem_bytes(m->host.nl, (int)m->host.tc5_steps.size(), m->tc5h_nstage, m->tc5h_nlstage);
+    CK(cudaFuncSetAttribute(k_prune_tc5h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->prune_tc5h_smem));
+    if (const char *e = getenv("PCSF_TC5_VARIANT")) m->tc5_half = strcmp(e, "half") == 0;
     if ((st = upload(m->host.bls_prog.data(), m->host.bls_prog.size() * sizeof(BlsNode), (void **)&m->d_bls_prog))) return st;
     if ((st = upload(m->host.bl.data(), m->host.bl.size() * 4, (void **)&m->d_bl))) return st;
     {
@@ -288,8 +298,8 @@ static pcsf_status dedup_and_prune(pcsf_model *m, const WinSpace &ws, uint32_t n
         ta.max_stack = m->host.max_stack;
         ta.first0 = m->host.tc5_first[0];
         ta.first1 = m->host.tc5_first[1];
-        ta.nstage = m->tc5_nstage;
-        ta.nlstage = m->tc5_nlstage;
+        ta.nstage = m->tc5_half ? m->tc5h_nstage : m->tc5_nstage;
+        ta.nlstage = m->tc5_half ? m->tc5h_nlstage : m->tc5_nlstage;
         ta.scratch = m->d_tc5_scratch;
         for (int w = 0; w < 2; ++w) {
             ta.pstream[w] = m->d_pstream_tc5[w];
@@ -299,7 +309,9 @@ static pcsf_status dedup_and_prune(pcsf_model *m, const WinSpace &ws, uint32_t n
         }
         const uint32_t mp = (nwin + 255) / 256;
         const unsigned gridt = std::min<uint32_t>((uint32_t)m->sm_count, std::max<uint32_t>(1u, mp));
-        m->launches++; k_prune_tc5<<<gridt, T5_THREADS, m->prune_tc5_smem, st>>>(ta);
+        m->launches++;
+        if (m->tc5_half) k_prune_tc5h<<<gridt, T5H_THREADS, m->prune_tc5h_smem, st>>>(ta);
+        else k_prune_tc5<<<gridt, T5_THREADS, m->prune_tc5_smem, st>>>(ta);
         CK(cudaGetLastError());
         if (m->timing) {
             CK(cudaEventRecord(m->ev[3], st));

@@ -59,7 +59,7 @@ __host__ __device__ inline size_t prune_tc5_smem_bytes(int nl, int n_steps, int 
     b += (size_t)2 * nl * 128;                              // leaf codon ids of both tiles
     b += (size_t)(((n_steps + 1) * 4 + 15) / 16) * 16;      // steps
     b += 2 * 64 * 8;                                        // pi
-    b += 32 * 8;                                            // mbarriers + TMEM base
+    b += 32 * 8;                                            // mbarriers + TMEM base (2*3 + 2*6 + 4 + 2 barriers)
     return b;
 }
 // Deepest rings that fit into one SM's shared memory.
@@ -82,8 +82,8 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
     uint64_t *empty = full + T5_MAX_NSTAGE;
     uint64_t *lfull = empty + T5_MAX_NSTAGE;
     uint64_t *lempty = lfull + T5_MAX_NLSTAGE;
-    uint64_t *a_ready = lempty + T5_MAX_NLSTAGE;   // [2] epilogue -> MMA: A of the step is in TMEM
-    uint64_t *d_ready = a_ready + 2;           // [2] MMA -> epilogue: D of the step is complete
+    uint64_t *a_ready = lempty + T5_MAX_NLSTAGE;   // [2 chains][2 halves] epilogue -> MMA: states 0..31 / 32..63 of the step's A are in TMEM
+    uint64_t *d_ready = a_ready + 4;           // [2] MMA -> epilogue: D of the step is complete
     uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(d_ready + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
     if (tid == 0) {
         for (int s = 0; s < T5_MAX_NSTAGE; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
         for (int s = 0; s < T5_MAX_NLSTAGE; ++s) { mbar_init(lfull + s, 1); mbar_init(lempty + s, 8); }
-        for (int c = 0; c < 2; ++c) { mbar_init(a_ready + c, 128); mbar_init(d_ready + c, 1); }
+        for (int c = 0; c < 2; ++c) { for (int k = 0; k < 2; ++k) mbar_init(a_ready + 2 * c + k, 128); mbar_init(d_ready + c, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 8) { tc5::tmem_alloc(tmem_base_slot, 512); tc5::tmem_relinquish(); }
@@ -152,19 +152,28 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
                         mbar_wait(full + st, (use / T5_NSTAGE) & 1);
                         const uint32_t sb = tc5::smem_addr(stage_buf + (size_t)st * T5_TILE_BYTES);
                         for (int c = 0; c < 2; ++c) {
-                            mbar_wait(a_ready + c, use & 1);
-                            T5_TRACE(2, s, 2 * c);
-                            tc5::fence_after_sync();
-                            if (tc5::elect_one()) {
-                                const uint32_t ta = tmem + c * 256 + (use & 1) * 128, td = tmem + c * 256 + ((use & 1) ^ 1) * 128;
+                            // k-steps 0..3 only need states 0..31 of A: they are issued while the epilogue threads still split and store
+                            // the other half (measured: 101.2 -> 95.8 ms per 8 Mi columns; four quarters: 98.6 ms, the extra
+                            // tcgen05.wait::st round trips cost more than the earlier start gains)
+                            const uint32_t ta = tmem + c * 256 + (use & 1) * 128, td = tmem + c * 256 + ((use & 1) ^ 1) * 128;
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    const uint64_t bd = tc5::smem_desc(sb + j * 4096, 128, 256);
-                                    tc5::mma_tf32_ts(td, ta + 8 * j, bd, idesc, j > 0);
-                                    tc5::mma_tf32_ts(td, ta + 64 + 8 * j, bd, idesc_hi, 1);      // lo(A) x hi(B) only
+                            for (int k = 0; k < 2; ++k) {
+                                mbar_wait(a_ready + 2 * c + k, use & 1);
+                                if (k == 0) T5_TRACE(2, s, 2 * c);
+                                tc5::fence_after_sync();
+                                if (tc5::elect_one()) {
+#pragma unroll
+                                    for (int j = 4 * k; j < 4 * k + 4; ++j) {
+                                        const uint64_t bd = tc5::smem_desc(sb + j * 4096, 128, 256);
+                                        tc5::mma_tf32_ts(td, ta + 8 * j, bd, idesc, j > 0);
+                                        tc5::mma_tf32_ts(td, ta + 64 + 8 * j, bd, idesc_hi, 1);      // lo(A) x hi(B) only
+                                    }
+                                    if (k == 1) {
+                                        tc5::commit(d_ready + c);
+                                        if (c == 1) tc5::commit(empty + st);
+                                    }
                                 }
-                                tc5::commit(d_ready + c);
-                                if (c == 1) tc5::commit(empty + st);
+                                __syncwarp();
                             }
                             __syncwarp();
                             T5_TRACE(2, s, 2 * c + 1);
@@ -272,12 +281,18 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
                             lo[i] = __float_as_uint(l.x);
                             lo[i + 1] = __float_as_uint(l.y);
                         }
+                        if (h == 2) {
+                            // states 0..31 are on their way: hand them to the MMA warp before storing the rest
+                            tc5::wait_st();
+                            tc5::fence_before_sync();
+                            mbar_arrive(a_ready + 2 * c);
+                        }
                         tc5::st16(areg + 16 * h, hi);
                         tc5::st16(areg + 64 + 16 * h, lo);
                     }
                     tc5::wait_st();
                     tc5::fence_before_sync();
-                    mbar_arrive(a_ready + c);
+                    mbar_arrive(a_ready + 2 * c + 1);
                 };
                 if (a.n_steps > 0) split_and_arrive(R, lane_base + (use & 1) * 128);
 

@@ -10,7 +10,6 @@
 // output does not depend on the thread or GPU count (the reference merges its per-job files in job order,
 // build_tracks.hpp:27-53,245-259).
 // --output-phylo / --output-regions: the PhyloCSF-HMM smoothing of the raw tracks stays on the host (hmm.hpp).
-// Not in this tool: the FIXED_MEAN strategy (score-msa --strategy fixed_mean).
 #include <cinttypes>
 #include <chrono>
 #include <condition_variable>
@@ -346,10 +345,16 @@ int main_score_msa(int argc, char **argv) {
     if (a.pos.size() < 2) die("usage: phylocsf_b200 score-msa [OPTIONS] <model> <alignments>...");
     const std::string strat = lower(a.str("strategy", "mle"));
     pcsf_strategy strategy;
+    bool fixed_mean = false;
     if (strat == "mle") strategy = PCSF_STRATEGY_MLE;
     else if (strat == "fixed") strategy = PCSF_STRATEGY_FIXED;
     else if (strat == "omega") strategy = PCSF_STRATEGY_OMEGA;
-    else die("--strategy %s is not part of this tool (MLE, FIXED and OMEGA are)", strat.c_str());
+    else if (strat == "fixed_mean") { strategy = PCSF_STRATEGY_FIXED; fixed_mean = true; }          // score_msa.hpp:314-325
+    else { printf("\033[31mPlease choose a valid strategy (MLE, FIXED or OMEGA)!\n\033[0m"); return -1; }
+    if (fixed_mean && (!a.has("genome-length") || !a.has("coding-exons"))) {
+        printf("\033[31mFor FIXED_MEAN you need to provide --genome-length and --coding-exons.\n\033[0m");
+        return -1;
+    }
     const bool comp_phylo = a.boolean("comp-phylo", true), comp_anc = a.boolean("comp-anc", false), comp_bls = true;   // no --comp-bls in the reference
     if (strategy == PCSF_STRATEGY_OMEGA && comp_anc) {          // score_msa.hpp:338-342
         printf("\033[31mThe ancestral sequence composition cannot be computed in the Omega mode!\n\033[0m");
@@ -362,6 +367,8 @@ int main_score_msa(int argc, char **argv) {
     Model model;
     load_model(model, a.pos[0], a.str("species"), a.str("mapping"));
     const int nl = model.nl();
+    Hmm hmm_model{};
+    if (fixed_mean) hmm_model = coding_hmm(estimate_hmm_params(a.str("coding-exons"), (uint32_t)strtoull(a.str("genome-length").c_str(), nullptr, 10)));
     std::vector<pcsf_model *> dev(workers_n);
     for (int t = 0; t < workers_n; ++t) dev[t] = create_device_model(model, t % gpus);
 
@@ -413,6 +420,34 @@ int main_score_msa(int argc, char **argv) {
                                                               comp_anc ? anc.data() : nullptr, comp_bls ? bls.data() : nullptr);
                         if (st == PCSF_ERR_BAD_CHAR) { fprintf(stderr, "%s\n", pcsf_last_error()); exit(37); }
                         if (st != PCSF_OK) die("pcsf_score_msa: %s", pcsf_last_error());
+                    }
+                    if (fixed_mean && n > 0 && comp_phylo) {
+                        // FIXED_MEAN (score_msa.hpp:136-213): the per-codon decibans of frame +1 (run_tracks) go through the
+                        // PhyloCSF-HMM as one contiguous run; the score is the mean posterior log-odds, summed in a float.
+                        // Per-codon scores come from the tracks entry point on the alignments laid side by side.
+                        int64_t Ltot = 0;
+                        std::vector<int64_t> col0(n);
+                        for (int i = 0; i < n; ++i) { col0[i] = Ltot; Ltot += len[i]; }
+                        std::vector<double> plus((size_t)std::max<int64_t>(Ltot - 2, 0)), minus(plus.size());
+                        if (Ltot > 2) {
+                            std::vector<uint8_t> mat((size_t)nl * Ltot);
+                            for (int i = 0; i < n; ++i)
+                                for (int sp = 0; sp < nl; ++sp)
+                                    if (len[i]) memcpy(mat.data() + (size_t)sp * Ltot + col0[i], blob.data() + off[i] + (size_t)sp * len[i], (size_t)len[i]);
+                            const pcsf_status st = pcsf_tracks(dev[t], mat.data(), Ltot, Ltot, PCSF_TRACKS_SCORES, plus.data(), minus.data(), nullptr, nullptr, nullptr);
+                            if (st != PCSF_OK) die("pcsf_tracks: %s", pcsf_last_error());
+                        }
+                        std::vector<double> scores, post;
+                        for (int i = 0; i < n; ++i) {
+                            scores.clear();
+                            for (int64_t k = 0; k < len[i] / 3; ++k) scores.push_back(plus[(size_t)(col0[i] + 3 * k)]);
+                            hmm_posterior_coding(hmm_model, scores, post);
+                            float sum = 0.0;
+                            uint64_t cnt = 0;
+                            for (double pc : post) sum += hmm_log_odds(pc);
+                            cnt += post.size();
+                            phylo[i] = sum / cnt;
+                        }
                     }
                     std::string text;
                     char v[64];
@@ -521,7 +556,7 @@ int main(int argc, char **argv) {
                "  phylocsf_b200 build-tracks [--output-raw-phylo BOOL] [--output-phylo BOOL] [--output-regions BOOL] [--genome-length INT]\n"
                "                             [--coding-exons FILE] [--power-threshold FLOAT] [--threads INT] [--gpus INT]\n"
                "                             [--precision f64|tc5|f32] [--output DIR] [--mapping FILE] [--species LIST] <model> <maf>...\n"
-               "  phylocsf_b200 score-msa    [--strategy MLE|FIXED|OMEGA] [--comp-phylo BOOL] [--comp-anc BOOL] [--threads INT] [--gpus INT]\n"
+               "  phylocsf_b200 score-msa    [--strategy MLE|FIXED|OMEGA|FIXED_MEAN] [--comp-phylo BOOL] [--comp-anc BOOL] [--threads INT] [--gpus INT]\n"
                "                             [--output DIR] [--mapping FILE] [--species LIST] <model> <maf>...\n");
         return argc < 2 ? 1 : 0;
     }

@@ -15,7 +15,7 @@ Fixtures (what each one pins that the reference's own goldens do not):
              exon list its tests.sh names is not shipped) -> 6 smoothed wigs + 6 region BED files
   smooth12   the same on tracks12 with tests/util.py:write_synthetic_exons (46 000 exons: gap subsampling path)
   msa29      score-msa, 29mammals reduced with --species to 12 leaves, 60 single-block alignments of 30..600 columns
-             (BASELINE config 5 shape), strategies fixed / mle (--comp-anc 1) and omega -> .scores files
+             (BASELINE config 5 shape), strategies fixed / mle (--comp-anc 1), omega and fixed_mean -> .scores files
 """
 import gzip
 import os
@@ -89,6 +89,10 @@ def main():
             ref("score-msa", "--threads", "8", "--strategy", strat, "--comp-phylo", "1", "--comp-anc", anc, "--species", SPECIES29,
                 "--output", os.path.join(tmp, "m29_" + strat), "29mammals", maf)
             shutil.copy(os.path.join(tmp, "m29_" + strat, "msa29.maf.scores"), os.path.join(OUT, f"msa29.{strat}.scores"))
+        # FIXED_MEAN: per-codon scores through the PhyloCSF-HMM (parameters from the synthetic exon list of smooth12)
+        ref("score-msa", "--threads", "8", "--strategy", "fixed_mean", "--comp-phylo", "1", "--comp-anc", "0", "--species", SPECIES29,
+            "--genome-length", "400000000", "--coding-exons", exons12, "--output", os.path.join(tmp, "m29_fm"), "29mammals", maf)
+        shutil.copy(os.path.join(tmp, "m29_fm", "msa29.maf.scores"), os.path.join(OUT, "msa29.fixed_mean.scores"))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

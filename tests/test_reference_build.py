@@ -209,3 +209,46 @@ def test_cli_score_msa_omega_vs_reference_msa29(golden_dir, tmp_path):
     assert max(d) ** 2 <= 0.1
     r = subprocess.run([BIN, "score-msa", "--strategy", "omega", "--comp-anc", "1", "29mammals", maf], capture_output=True, text=True)
     assert r.returncode != 0 and "Omega mode" in r.stdout
+
+
+@pytest.mark.gpu
+def test_cli_score_msa_fixed_mean_vs_reference_msa29(golden_dir, tmp_path):
+    """score-msa --strategy fixed_mean (score_msa.hpp:136-213): per-codon decibans from the CUDA tracks path through the host's
+    PhyloCSF-HMM, mean posterior log-odds per alignment — against the reference's own output."""
+    from tests.util import write_synthetic_exons
+    R = os.path.join(golden_dir, "ref-generated")
+    maf = _gunzip(os.path.join(R, "msa29.maf.gz"), os.path.join(str(tmp_path), "msa29.maf"))
+    exons = os.path.join(str(tmp_path), "exons.txt")
+    write_synthetic_exons(exons)
+    out = os.path.join(str(tmp_path), "o")
+    subprocess.run([BIN, "score-msa", "--strategy", "fixed_mean", "--species", SPECIES29, "--genome-length", "400000000", "--coding-exons", exons,
+                    "--output", out, "29mammals", maf], check=True, capture_output=True)
+    ours, gold = _rows(os.path.join(out, "msa29.maf.scores")), _rows(os.path.join(R, "msa29.fixed_mean.scores"))
+    assert len(ours) == len(gold)
+    exact = 0
+    for o, g in zip(ours, gold):
+        assert o[:4] == g[:4] and o[5] == g[5]
+        assert abs(float(o[4]) - float(g[4])) <= 1e-4
+        exact += o[4] == g[4]
+    assert exact >= len(gold) - 2
+    r = subprocess.run([BIN, "score-msa", "--strategy", "fixed_mean", "29mammals", maf], capture_output=True, text=True)
+    assert r.returncode != 0 and "FIXED_MEAN" in r.stdout
+
+
+@pytest.mark.gpu
+def test_tc5_half_variant_matches(golden_dir, tmp_path):
+    """The experimental 16-epilogue-warp tcgen05 kernel (PCSF_TC5_VARIANT=half) gives the same tracks as the default one to the
+    printed digit (two threads per window only change the order of the final 64-term sum)."""
+    R = os.path.join(golden_dir, "ref-generated")
+    maf = _gunzip(os.path.join(R, "tracks12.maf.gz"), os.path.join(str(tmp_path), "tracks12.maf"))
+    outs = []
+    for variant in ("base", "half"):
+        out = os.path.join(str(tmp_path), "o_" + variant)
+        subprocess.run([BIN, "build-tracks", "--threads", "2", "--precision", "tc5", "--output", out, "12flies", maf], check=True, capture_output=True,
+                       env=dict(os.environ, PCSF_TC5_VARIANT=variant))
+        outs.append(out)
+    for n in WIGS:
+        a = open(os.path.join(outs[0], n)).read().split("\n")
+        b = open(os.path.join(outs[1], n)).read().split("\n")
+        assert len(a) == len(b)
+        assert sum(x != y for x, y in zip(a, b)) <= len(a) // 1000 + 1

@@ -38,6 +38,26 @@ def flops_per_pruning(nl: int) -> int:
     return 2 * 64 * 64 * (nl - 2) + 64 * (nl - 1) + 128
 
 
+def hbm_passes(tstats, nl, B, Wn):
+    peak = 6458.7
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    alg = {"k_pack": ("ms_pack", 2 * nl * B),                       # ASCII in, codes out
+           "k_keys_tracks": ("ms_hash", nl * B + 32 * B),           # codes in, two 128-bit keys per column out
+           "dedup (insert/resolve/scan/finalize)": ("ms_dedup", 40 * 2 * Wn),
+           "k_scatter_tracks": ("ms_scatter", 24 * 2 * Wn),
+           "k_bls": ("ms_bls", nl * B + 8 * B)}
+    out = {}
+    for k, (key, nbytes) in alg.items():
+        ms = tstats.get(key) or 0.0
+        if ms > 0:
+            gbs = nbytes / (ms * 1e-3) / 1e9
+            out[k] = {"ms": ms, "bytes": nbytes, "gbs": gbs, "frac_of_hbm_peak": gbs / peak}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ CPU arm
 _W = {}
 
@@ -386,6 +406,9 @@ def main():
                          "flop_per_launch": flop_per_launch, "ms_per_launch": ms_per_launch,
                          "prunings_per_launch": tstats["n_unique"] * 2 / n_prune_launch},
             "stages_ms": {k: tstats[k] for k in ("ms_pack", "ms_hash", "ms_dedup", "ms_prune", "ms_scatter", "ms_bls")},
+            # the HBM-bound passes around the pruning kernel: ALGORITHMIC bytes / measured time, against
+            # MEASURED_PEAKS.json's copy bandwidth
+            "hbm_passes": hbm_passes(tstats, nl, B, Wn),
             "checksum": checksum,
             "other_precisions": other,
         }

@@ -34,18 +34,18 @@ __global__ void k_pack(const uint8_t *__restrict__ seqs, int64_t L, int64_t ld_i
          i += (int64_t)gridDim.x * blockDim.x * 16) {
         uint32_t out[4];
         if (vec && i + 16 <= L) {
+            // four bytes per SIMD-in-register step: a data-dependent index into the constant-memory table would serialise the
+            // warp (32 different addresses per load); byte-wise compares do not
             const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + i));
             const uint32_t in[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                uint32_t r = 0;
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const uint32_t c = c_dna_lut[(in[k] >> (8 * b)) & 0xff];
-                    local_bad |= (c == 255);
-                    r |= (c == 255 ? 4u : c) << (8 * b);
-                }
-                out[k] = r;
+                const uint32_t w = in[k], u = w | 0x20202020u;          // lower case (translation.hpp:29-53 accepts both)
+                const uint32_t isc = __vcmpeq4(u, 0x63636363u), isg = __vcmpeq4(u, 0x67676767u), ist = __vcmpeq4(u, 0x74747474u);
+                const uint32_t acgt = __vcmpeq4(u, 0x61616161u) | isc | isg | ist;
+                const uint32_t gap = __vcmpeq4(u, 0x6e6e6e6eu) | __vcmpeq4(w, 0x2e2e2e2eu) | __vcmpeq4(w, 0x2d2d2d2du);   // N n . -
+                local_bad |= (~(acgt | gap)) != 0u;
+                out[k] = (isc & 0x01010101u) | (isg & 0x02020202u) | (ist & 0x03030303u) | (~acgt & 0x04040404u);
             }
         } else {
 #pragma unroll

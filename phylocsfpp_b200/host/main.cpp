@@ -369,8 +369,18 @@ int main_score_msa(int argc, char **argv) {
     const int nl = model.nl();
     Hmm hmm_model{};
     if (fixed_mean) hmm_model = coding_hmm(estimate_hmm_params(a.str("coding-exons"), (uint32_t)strtoull(a.str("genome-length").c_str(), nullptr, 10)));
+    const auto t_start = std::chrono::steady_clock::now();
+    auto since = [&](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count(); };
     std::vector<pcsf_model *> dev(workers_n);
-    for (int t = 0; t < workers_n; ++t) dev[t] = create_device_model(model, t % gpus);
+    {
+        std::vector<std::thread> th;          // model preparation is host work (eigensystem, all P(t), uploads): one thread per handle
+        for (int t = 0; t < workers_n; ++t) th.emplace_back([&, t] { dev[t] = create_device_model(model, t % gpus); });
+        for (auto &x : th) x.join();
+    }
+    const double t_models = since(t_start);
+    double t_scan = 0.0, t_parse = 0.0, t_gpu = 0.0, t_format = 0.0;
+    std::mutex stat_mu;
+    int64_t total_aln = 0;
 
     for (size_t fi = 1; fi < a.pos.size(); ++fi) {
         const std::string &path = a.pos[fi];
@@ -386,7 +396,9 @@ int main_score_msa(int argc, char **argv) {
         if (comp_bls) fprintf(out, "\tbls-score");
         fprintf(out, "\n");
 
+        const auto s0 = std::chrono::steady_clock::now();
         MafFile maf(path, model, false, threads);
+        t_scan += since(s0);
         warn_unresolved(maf);
         const std::vector<MafFile::Chain> &chains = maf.chains();
         const size_t BATCH = 4096;
@@ -403,6 +415,7 @@ int main_score_msa(int argc, char **argv) {
                     std::vector<uint8_t> blob;
                     std::vector<int64_t> off, len;
                     std::vector<std::string> head;
+                    const auto p0 = std::chrono::steady_clock::now();
                     for (size_t ci = c0; ci < c1; ++ci) {
                         if (chains[ci].ref_id < 0) continue;
                         maf.read_chain(chains[ci], aln, nullptr);
@@ -415,6 +428,8 @@ int main_score_msa(int argc, char **argv) {
                     const int n = (int)off.size();
                     std::vector<float> phylo(n, NAN), anc(n, NAN), bls(n, NAN);
                     if (blob.empty()) blob.push_back('N');
+                    const double my_parse = since(p0);
+                    const auto g0 = std::chrono::steady_clock::now();
                     if (n > 0) {
                         const pcsf_status st = pcsf_score_msa(dev[t], strategy, n, blob.data(), off.data(), len.data(), (comp_phylo || comp_anc) ? phylo.data() : nullptr,
                                                               comp_anc ? anc.data() : nullptr, comp_bls ? bls.data() : nullptr);
@@ -449,6 +464,8 @@ int main_score_msa(int argc, char **argv) {
                             phylo[i] = sum / cnt;
                         }
                     }
+                    const double my_gpu = since(g0);
+                    const auto f0 = std::chrono::steady_clock::now();
                     std::string text;
                     char v[64];
                     for (int i = 0; i < n; ++i) {
@@ -461,6 +478,8 @@ int main_score_msa(int argc, char **argv) {
                     std::vector<std::string> one(1);
                     one[0] = std::move(text);
                     sink.put(bi, std::move(one));
+                    std::lock_guard<std::mutex> g(stat_mu);
+                    t_parse += my_parse; t_gpu += my_gpu; t_format += since(f0); total_aln += n;
                 }
             });
         for (size_t bi = 0; bi < nbatch; ++bi) {
@@ -471,6 +490,10 @@ int main_score_msa(int argc, char **argv) {
         fclose(out);
     }
     printf("Done!\n");
+    if (getenv("PCSF_HOST_STATS"))
+        printf("{\"alignments\": %" PRId64 ", \"seconds\": %.3f, \"model_seconds\": %.3f, \"scan_seconds\": %.3f, \"parse_seconds_sum\": %.3f, "
+               "\"gpu_call_seconds_sum\": %.3f, \"format_seconds_sum\": %.3f, \"workers\": %d}\n",
+               total_aln, since(t_start), t_models, t_scan, t_parse, t_gpu, t_format, workers_n);
     for (pcsf_model *m : dev) pcsf_model_destroy(m);
     (void)nl;
     return 0;

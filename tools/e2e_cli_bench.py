@@ -50,10 +50,17 @@ def main():
             open(maf, "rb").read()
             species = "Human,Chimp,Mouse,Dog,Cow,Horse,Elephant,Armadillo,Rat,Rabbit,Cat,Megabat"
             for strat in ("fixed", "mle"):
-                dt, _ = run([BIN, "score-msa", "--strategy", strat, "--comp-anc", "1", "--gpus", str(gpus), "--species", species, "--output",
-                             os.path.join(tmp, "s_" + strat), "29mammals", maf])
+                dt, st = run([BIN, "score-msa", "--strategy", strat, "--comp-anc", "1", "--gpus", str(gpus), "--species", species, "--output",
+                              os.path.join(tmp, "s_" + strat), "29mammals", maf])
                 res["score_msa_" + strat] = {"maf": info, "process_seconds": dt, "alignments_per_s": info["blocks"] / dt,
-                                             "columns_per_s": info["columns"] / dt}
+                                             "columns_per_s": info["columns"] / dt, "tool_stats": st}
+            # OMEGA: ~200 likelihood evaluations and ~100 eigendecompositions per alignment -> a tenth of the file
+            maf_o = os.path.join(tmp, "blocks_omega.maf")
+            info_o = write_synth_maf(maf_o, load_model("29mammals"), max(30000, n_msa // 10), seed=4, loguniform_blocks=(30, 600))
+            dt, st = run([BIN, "score-msa", "--strategy", "omega", "--gpus", str(gpus), "--species", species, "--output", os.path.join(tmp, "s_omega"),
+                         "29mammals", maf_o])
+            res["score_msa_omega"] = {"maf": info_o, "process_seconds": dt, "alignments_per_s": info_o["blocks"] / dt, "columns_per_s": info_o["columns"] / dt,
+                                      "tool_stats": st}
     print(json.dumps(res))
 
 

@@ -1,0 +1,30 @@
+"""bench.py's driver contract on the CPU-runnable arm: `--impl reference` prints exactly ONE JSON line on stdout with the
+keys the driver reads (metric, value, unit, n_gpus, steps, warmup, ms_per_step, impl, cpu_baseline, e2e)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_json_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-sample", "3000"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "columns/s" and d["higher_is_better"] is True and d["n_gpus"] == 1
+    assert d["steps"] == 1 and d["warmup"] == 0 and d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "columns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["metric"].startswith("MAF columns/sec") and d["config"]["model"] == "58mammals"
+    # the kind is "reference" exactly when the shim-built reference binary is there
+    assert (d["cpu_baseline"]["kind"] == "reference") == os.path.exists(os.path.join(ROOT, "oracle", "_ref", "phylocsf_ref"))
+
+
+def test_other_ranks_of_the_reference_arm_exit_quietly():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=120, cwd=ROOT, env=dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2"))
+    assert r.returncode == 0 and r.stdout.strip() == ""

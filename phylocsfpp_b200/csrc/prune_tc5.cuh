@@ -261,6 +261,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
 #endif
                 // A = split(alpha): per-window normalisation by an exact power of two, then TF32 hi + lo (hi = the 19 bits
                 // the tensor core reads, lo = the exact remainder); hands the step to the MMA warp
+                float amax_prev = 0.f;          // largest entry of the A that was handed over last (in [1, 2), or 0)
                 auto split_and_arrive = [&](const float (&V)[64], uint32_t areg) {
                     float mx = 0.f;
 #pragma unroll
@@ -269,6 +270,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
                     const float sc = __uint_as_float((uint32_t)(127 - e) << 23);
                     const float2 sc2 = make_float2(sc, sc);
                     E += e;
+                    amax_prev = mx * sc;
 #pragma unroll
                     for (int h = 0; h < 4; ++h) {
                         uint32_t hi[16], lo[16];
@@ -327,35 +329,36 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
                     T5_TRACE(c, s, 2);
                     tc5::fence_after_sync();
                     const uint32_t dreg = lane_base + ((use & 1) ^ 1) * 128;     // D_s; A_{s+1} overwrites it in place
-                    {
-                        uint32_t x0[32], y0[32], x1[32], y1[32];
-                        tc5::ld32(dreg, x0);
-                        tc5::ld32(dreg + 64, y0);
-                        tc5::ld32(dreg + 32, x1);
-                        tc5::ld32(dreg + 96, y1);
-                        tc5::wait_ld();
-                        // msg = D[0:64] + D[64:128]
+                    if (post == T5_PUSH_CHERRY || s + 1 == a.n_steps) {
+                        // the message itself is needed (pushed onto the stack / dotted with pi): load all of it
+                        {
+                            uint32_t x0[32], y0[32], x1[32], y1[32];
+                            tc5::ld32(dreg, x0);
+                            tc5::ld32(dreg + 64, y0);
+                            tc5::ld32(dreg + 32, x1);
+                            tc5::ld32(dreg + 96, y1);
+                            tc5::wait_ld();
+                            // msg = D[0:64] + D[64:128]
 #pragma unroll
-                        for (int i = 0; i < 32; i += 2) {
-                            const float2 v0 = __fadd2_rn(make_float2(__uint_as_float(x0[i]), __uint_as_float(x0[i + 1])),
-                                                         make_float2(__uint_as_float(y0[i]), __uint_as_float(y0[i + 1])));
-                            const float2 v1 = __fadd2_rn(make_float2(__uint_as_float(x1[i]), __uint_as_float(x1[i + 1])),
-                                                         make_float2(__uint_as_float(y1[i]), __uint_as_float(y1[i + 1])));
-                            R[i] = v0.x; R[i + 1] = v0.y; R[32 + i] = v1.x; R[32 + i + 1] = v1.y;
+                            for (int i = 0; i < 32; i += 2) {
+                                const float2 v0 = __fadd2_rn(make_float2(__uint_as_float(x0[i]), __uint_as_float(x0[i + 1])),
+                                                             make_float2(__uint_as_float(y0[i]), __uint_as_float(y0[i + 1])));
+                                const float2 v1 = __fadd2_rn(make_float2(__uint_as_float(x1[i]), __uint_as_float(x1[i + 1])),
+                                                             make_float2(__uint_as_float(y1[i]), __uint_as_float(y1[i + 1])));
+                                R[i] = v0.x; R[i + 1] = v0.y; R[32 + i] = v1.x; R[32 + i + 1] = v1.y;
+                            }
                         }
-                    }
-                    if (post == T5_PUSH_CHERRY) {
-                        // the next GEMM's input is the cherry (already in L): hand it over first, then push the message
-                        const int Epush = E;
-                        E = 0;
-                        split_and_arrive(L, dreg);
-                        float4 *e4 = reinterpret_cast<float4 *>(stk + (size_t)sp * T5_STACK_ENTRY_FLOATS);
+                        if (post == T5_PUSH_CHERRY) {
+                            // the next GEMM's input is the cherry (already in L): hand it over first, then push the message
+                            const int Epush = E;
+                            E = 0;
+                            split_and_arrive(L, dreg);
+                            float4 *e4 = reinterpret_cast<float4 *>(stk + (size_t)sp * T5_STACK_ENTRY_FLOATS);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) __stcg(e4 + j * 128 + t, make_float4(R[4 * j], R[4 * j + 1], R[4 * j + 2], R[4 * j + 3]));
-                        __stcg(reinterpret_cast<int *>(stk + (size_t)sp * T5_STACK_ENTRY_FLOATS + 8192) + t, Epush);
-                        ++sp;
-                    } else {
-                        if (post == T5_MUL_LEAF || post == T5_POP_MUL) {
+                            for (int j = 0; j < 16; ++j) __stcg(e4 + j * 128 + t, make_float4(R[4 * j], R[4 * j + 1], R[4 * j + 2], R[4 * j + 3]));
+                            __stcg(reinterpret_cast<int *>(stk + (size_t)sp * T5_STACK_ENTRY_FLOATS + 8192) + t, Epush);
+                            ++sp;
+                        } else if (post == T5_MUL_LEAF || post == T5_POP_MUL) {
 #pragma unroll
                             for (int i = 0; i < 64; i += 2) {
                                 const float2 v = __fmul2_rn(make_float2(R[i], R[i + 1]), make_float2(L[i], L[i + 1]));
@@ -363,7 +366,62 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
                             }
                             E += Epop;
                         }
-                        if (s + 1 < a.n_steps) split_and_arrive(R, dreg);
+                    } else {
+                        // Streamed hand-over.  Any power of two is an exact scale, so the normalisation does not have to wait
+                        // for this message's own maximum: every entry is <= the largest entry of the A it was computed from
+                        // (rows of P sum to <= 1, leaf and sibling factors are <= the scale they carry), hence the exponent of
+                        // that previous maximum keeps the new A below 2, and how far below is corrected one step later.  Without
+                        // a separate max pass the scale is folded into the combine (streaming the TMEM loads in two halves was measured slower:
+                        // a second tcgen05.wait::ld round trip costs more than the overlap gains, 114 against 97 ms).
+                        const bool mul = post == T5_MUL_LEAF || post == T5_POP_MUL;
+                        const int e = amax_prev > 0.f ? (int)((__float_as_uint(amax_prev) >> 23) & 0xff) - 127 : 0;
+                        const float sc = __uint_as_float((uint32_t)(127 - e) << 23);
+                        const float2 sc2 = make_float2(sc, sc);
+                        E += e + (mul ? Epop : 0);
+                        float amax = 0.f;
+                        {
+                            uint32_t x0[32], y0[32], x1[32], y1[32];
+                            tc5::ld32(dreg, x0);
+                            tc5::ld32(dreg + 64, y0);
+                            tc5::ld32(dreg + 32, x1);
+                            tc5::ld32(dreg + 96, y1);
+                            tc5::wait_ld();
+#pragma unroll
+                            for (int i = 0; i < 32; i += 2) {
+                                float2 v0 = __fadd2_rn(make_float2(__uint_as_float(x0[i]), __uint_as_float(x0[i + 1])),
+                                                       make_float2(__uint_as_float(y0[i]), __uint_as_float(y0[i + 1])));
+                                float2 v1 = __fadd2_rn(make_float2(__uint_as_float(x1[i]), __uint_as_float(x1[i + 1])),
+                                                       make_float2(__uint_as_float(y1[i]), __uint_as_float(y1[i + 1])));
+                                if (mul) {
+                                    v0 = __fmul2_rn(v0, make_float2(L[i], L[i + 1]));
+                                    v1 = __fmul2_rn(v1, make_float2(L[32 + i], L[32 + i + 1]));
+                                }
+                                v0 = __fmul2_rn(v0, sc2);
+                                v1 = __fmul2_rn(v1, sc2);
+                                amax = fmaxf(amax, fmaxf(fmaxf(v0.x, v0.y), fmaxf(v1.x, v1.y)));
+                                R[i] = v0.x; R[i + 1] = v0.y; R[32 + i] = v1.x; R[32 + i + 1] = v1.y;
+                            }
+                        }
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            uint32_t hi[16], lo[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                hi[i] = __float_as_uint(R[16 * h + i]) & 0xffffe000u;
+                                lo[i] = __float_as_uint(R[16 * h + i] - __uint_as_float(hi[i]));
+                            }
+                            if (h == 2) {
+                                tc5::wait_st();
+                                tc5::fence_before_sync();
+                                mbar_arrive(a_ready + 2 * c);
+                            }
+                            tc5::st16(dreg + 16 * h, hi);
+                            tc5::st16(dreg + 64 + 16 * h, lo);
+                        }
+                        tc5::wait_st();
+                        tc5::fence_before_sync();
+                        mbar_arrive(a_ready + 2 * c + 1);
+                        amax_prev = amax;
                     }
                     T5_TRACE(c, s, 3);
                 }

@@ -366,9 +366,16 @@ def main():
         except Exception:
             pass
         traffic = None
+        traffic_note = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_prune_traffic.json"))).get(
-                {"f64": "dram_bytes_per_launch", "f32": "dram_bytes_per_launch_f32", "tc5": "dram_bytes_per_launch_tc5"}[args.precision])
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_prune_traffic.json")))
+            traffic = tj.get({"f64": "dram_bytes_per_launch", "f32": "dram_bytes_per_launch_f32", "tc5": "dram_bytes_per_launch_tc5"}[args.precision])
+            cap_cols = tj.get("tc5_columns_per_captured_launch") if args.precision == "tc5" else None
+            if traffic and cap_cols:
+                # the ncu --set full capture ran on a smaller batch; DRAM traffic of this kernel (leaf codes in, log z out) is linear
+                # in the columns of a launch
+                traffic = traffic * (B / n_prune_launch) / cap_cols
+                traffic_note = f"dram__bytes_read+write of one ncu --set full capture at {cap_cols} columns per launch, scaled to {B // n_prune_launch}"
         except Exception:
             pass
         if args.precision == "f64":
@@ -401,7 +408,7 @@ def main():
             "gpu_launches": stats["n_launches"] * args.steps,
             "clocks": clocks,
             "roofline": {"kernel": kernel, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": traffic, "executed_tflops": executed,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "executed_tflops": executed,
                          "executed_frac": executed / peak, "peak_source": peak_source,
                          "flop_per_launch": flop_per_launch, "ms_per_launch": ms_per_launch,
                          "prunings_per_launch": tstats["n_unique"] * 2 / n_prune_launch},

@@ -95,23 +95,69 @@ __device__ __forceinline__ uint64_t fmix64(uint64_t k) {
     return k;
 }
 
-// k_keys mode 0: one thread per column offset, both strands (they share the three byte loads).
+// 128-bit site-pattern key of one window: the nl codon ids (7 bits each) are packed nine to a 64-bit word and every full word is
+// folded into two independent multiply-xor lanes — two 64-bit multiplies per nine species instead of per species (the kernel is bound
+// by these integer multiplies, not by bytes).  Pattern identity = equality of the (fmix64(h1), fmix64(h2)) pair.
+struct PatternHash {
+    uint64_t h1 = 0x9E3779B97F4A7C15ULL, h2 = 0xC2B2AE3D27D4EB4FULL, acc = 0;
+    __device__ __forceinline__ void fold() {
+        h1 = (h1 ^ acc) * 0x100000001B3ULL;
+        h1 ^= h1 >> 32;
+        h2 = (h2 + acc + 1) * 0xFF51AFD7ED558CCDULL;
+        h2 ^= h2 >> 29;
+        acc = 0;
+    }
+    __device__ __forceinline__ void add(uint32_t codon) { acc = (acc << 7) | codon; }
+};
+
+// k_keys mode 0: both strands of FOUR consecutive column offsets per thread (two aligned 32-bit loads per species give the six
+// bytes they share).  Needs rows and c0 that are multiples of four (rows are padded to 16, chunk starts are multiples of four).
 __global__ void k_keys_tracks(WinSpace ws, int64_t ncols, ulonglong2 *__restrict__ klo, ulonglong2 *__restrict__ khi) {
+    const int64_t t4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (t4 >= ncols) return;
+    const uint8_t *p = ws.codes + ws.c0 + t4;
+    PatternHash hp[4], hm[4];
+    int inword = 0;
+    for (int s = 0; s < ws.nl; ++s, p += ws.ld) {
+        const uint32_t w0 = *reinterpret_cast<const uint32_t *>(p), w1 = *reinterpret_cast<const uint32_t *>(p + 4);   // bytes t4 .. t4+7
+        const uint32_t b[6] = {w0 & 0xff, (w0 >> 8) & 0xff, (w0 >> 16) & 0xff, w0 >> 24, w1 & 0xff, (w1 >> 8) & 0xff};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            hp[j].add(codon_plus(b[j], b[j + 1], b[j + 2]));
+            hm[j].add(codon_minus(b[j], b[j + 1], b[j + 2]));
+        }
+        if (++inword == 9) {
+            inword = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { hp[j].fold(); hm[j].fold(); }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        hp[j].fold(); hm[j].fold();
+        if (t4 + j < ncols) {
+            klo[t4 + j] = make_ulonglong2(fmix64(hp[j].h1), fmix64(hm[j].h1));
+            khi[t4 + j] = make_ulonglong2(fmix64(hp[j].h2), fmix64(hm[j].h2));
+        }
+    }
+}
+
+// The same keys, one thread per column offset, for a window space whose first column is not a multiple of four.
+__global__ void k_keys_tracks_unaligned(WinSpace ws, int64_t ncols, ulonglong2 *__restrict__ klo, ulonglong2 *__restrict__ khi) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ncols) return;
     const uint8_t *p = ws.codes + ws.c0 + t;
-    uint64_t a1 = 0x9E3779B97F4A7C15ULL, a2 = 0xC2B2AE3D27D4EB4FULL;
-    uint64_t b1 = a1, b2 = a2;
+    PatternHash hp, hm;
+    int inword = 0;
     for (int s = 0; s < ws.nl; ++s, p += ws.ld) {
         const uint32_t x0 = p[0], x1 = p[1], x2 = p[2];
-        const uint64_t cp = codon_plus(x0, x1, x2), cm = codon_minus(x0, x1, x2);
-        a1 = (a1 ^ cp) * 0x100000001B3ULL;
-        a2 = (a2 + cp + 1) * 0xFF51AFD7ED558CCDULL; a2 ^= a2 >> 29;
-        b1 = (b1 ^ cm) * 0x100000001B3ULL;
-        b2 = (b2 + cm + 1) * 0xFF51AFD7ED558CCDULL; b2 ^= b2 >> 29;
+        hp.add(codon_plus(x0, x1, x2));
+        hm.add(codon_minus(x0, x1, x2));
+        if (++inword == 9) { inword = 0; hp.fold(); hm.fold(); }
     }
-    klo[t] = make_ulonglong2(fmix64(a1), fmix64(b1));
-    khi[t] = make_ulonglong2(fmix64(a2), fmix64(b2));
+    hp.fold(); hm.fold();
+    klo[t] = make_ulonglong2(fmix64(hp.h1), fmix64(hm.h1));
+    khi[t] = make_ulonglong2(fmix64(hp.h2), fmix64(hm.h2));
 }
 
 // k_keys mode 1: one thread per listed window, '+' strand only.

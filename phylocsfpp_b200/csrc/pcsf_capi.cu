@@ -257,8 +257,13 @@ static pcsf_status dedup_and_prune(pcsf_model *m, const WinSpace &ws, uint32_t n
         CK(m->khi.reserve((size_t)nwin * 8));
         if (ws.mode == 0) {
             const int64_t ncols = nwin / 2;
-            m->launches++; k_keys_tracks<<<(unsigned)((ncols + TB - 1) / TB), TB, 0, st>>>(ws, ncols, m->klo.as<ulonglong2>(),
-                                                                           m->khi.as<ulonglong2>());
+            m->launches++;
+            if ((ws.c0 & 3) == 0 && (ws.ld & 3) == 0 && (reinterpret_cast<uintptr_t>(ws.codes) & 3) == 0) {
+                const int64_t nthr = (ncols + 3) / 4;
+                k_keys_tracks<<<(unsigned)((nthr + TB - 1) / TB), TB, 0, st>>>(ws, ncols, m->klo.as<ulonglong2>(), m->khi.as<ulonglong2>());
+            } else {
+                k_keys_tracks_unaligned<<<(unsigned)((ncols + TB - 1) / TB), TB, 0, st>>>(ws, ncols, m->klo.as<ulonglong2>(), m->khi.as<ulonglong2>());
+            }
         } else {
             m->launches++; k_keys_list<<<nblk, TB, 0, st>>>(ws, nwin, m->klo.as<uint64_t>(), m->khi.as<uint64_t>());
         }

@@ -69,6 +69,13 @@ typedef struct pcsf_model pcsf_model;
 pcsf_status pcsf_model_create(const pcsf_model_desc *desc, int device, pcsf_model **out);
 void pcsf_model_destroy(pcsf_model *m);
 
+/* Page-locked host memory for the buffers handed to pcsf_tracks / pcsf_score_msa (optional: any host pointer works; pinned ones are
+ * copied by DMA without staging — bench.py's e2e leg uses pinned buffers).  The reference's caller owns Data / alignment_t / the output
+ * vectors (build_tracks.hpp:60, 74-79); here the caller owns these buffers.  Pinning costs ~0.4 ms per MB: worth it for buffers that
+ * are reused across many calls (measured: the command line host on a 10 M-column file is faster with pageable vectors). */
+void *pcsf_alloc_pinned(size_t bytes);
+void pcsf_free_pinned(void *p);
+
 /* Thread-local description of the last error returned on this thread. */
 const char *pcsf_last_error(void);
 int pcsf_abi_version(void);

@@ -34,7 +34,7 @@ STRATEGY_OMEGA = 2
 EXPORTS = [
     "pcsf_model_create", "pcsf_model_destroy", "pcsf_last_error", "pcsf_abi_version", "pcsf_tracks",
     "pcsf_tracks_device", "pcsf_tracks_device_finish", "pcsf_set_chunk_columns", "pcsf_set_timing",
-    "pcsf_score_msa", "pcsf_model_get",
+    "pcsf_score_msa", "pcsf_model_get", "pcsf_alloc_pinned", "pcsf_free_pinned",
 ]
 
 
@@ -73,6 +73,10 @@ def load():
     L = C.CDLL(LIB_PATH)
     L.pcsf_last_error.restype = C.c_char_p
     L.pcsf_abi_version.restype = C.c_int
+    L.pcsf_alloc_pinned.restype = C.c_void_p
+    L.pcsf_alloc_pinned.argtypes = [C.c_size_t]
+    L.pcsf_free_pinned.restype = None
+    L.pcsf_free_pinned.argtypes = [C.c_void_p]
     L.pcsf_model_create.argtypes = [C.POINTER(ModelDesc), C.c_int, C.POINTER(C.c_void_p)]
     L.pcsf_model_destroy.argtypes = [C.c_void_p]
     L.pcsf_model_destroy.restype = None

@@ -522,6 +522,13 @@ extern "C" pcsf_status pcsf_tracks(pcsf_model *m, const uint8_t *seqs, int64_t L
     return PCSF_OK;
 }
 
+extern "C" void *pcsf_alloc_pinned(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { g_err = "cudaHostAlloc failed"; return nullptr; }
+    return p;
+}
+extern "C" void pcsf_free_pinned(void *p) { if (p) cudaFreeHost(p); }
+
 // ---- score-msa -------------------------------------------------------------------------------------
 extern "C" pcsf_status pcsf_score_msa(pcsf_model *m, pcsf_strategy strategy, int32_t n_aln, const uint8_t *seqs,
                                       const int64_t *offset, const int64_t *len, float *phylo, float *anc, float *bls) {

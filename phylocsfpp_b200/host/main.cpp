@@ -147,6 +147,10 @@ int main_build_tracks(int argc, char **argv) {
     make_pools(model, gpus, 2, pools);
     std::vector<std::vector<uint8_t>> seen(threads, std::vector<uint8_t>(nl, 0));
     double t_parse = 0.0, t_format = 0.0, t_scan = 0.0;
+    const bool dev_timing = getenv("PCSF_HOST_TIMING") != nullptr;          // per-stage CUDA-event times of every library call (diagnostic)
+    if (dev_timing) for (auto &p : pools) for (pcsf_model *dm : p->all) pcsf_set_timing(dm, 1);
+    double dev_ms[6] = {0, 0, 0, 0, 0, 0};
+    int64_t dev_unique = 0, dev_windows = 0;
     static const char *kFrames[6] = {"+1", "+2", "+3", "-1", "-2", "-3"};
     int64_t total_cols = 0;
     double t_gpu = 0.0;
@@ -223,9 +227,15 @@ int main_build_tracks(int argc, char **argv) {
                         ModelPool &pool = *pools[gi % gpus];
                         pcsf_model *dm = pool.acquire();
                         const auto g0 = now();
+                        pcsf_tracks_stats cs{};
                         const pcsf_status st = pcsf_tracks(dm, src, Ltot, Ltot, PCSF_TRACKS_BLS | (raw ? PCSF_TRACKS_SCORES : 0) | pflag,
-                                                           plus.data(), minus.data(), bls.data(), nullptr, nullptr);
+                                                           plus.data(), minus.data(), bls.data(), nullptr, &cs);
                         my_gpu += secs(g0, now());
+                        if (dev_timing) {
+                            std::lock_guard<std::mutex> g(gpu_time_mu);
+                            dev_ms[0] += cs.ms_pack; dev_ms[1] += cs.ms_hash; dev_ms[2] += cs.ms_dedup; dev_ms[3] += cs.ms_prune; dev_ms[4] += cs.ms_scatter;
+                            dev_ms[5] += cs.ms_bls; dev_unique += cs.n_unique; dev_windows += cs.n_windows;
+                        }
                         pool.release(dm);
                         if (st == PCSF_ERR_BAD_CHAR) { fprintf(stderr, "%s\n", pcsf_last_error()); exit(37); }      // translation.hpp:46-51
                         if (st != PCSF_OK) die("pcsf_tracks: %s", pcsf_last_error());
@@ -328,6 +338,9 @@ int main_build_tracks(int argc, char **argv) {
         printf("{\"columns\": %" PRId64 ", \"seconds\": %.3f, \"columns_per_s\": %.1f, \"threads\": %d, \"gpus\": %d, \"scan_seconds\": %.3f, "
                "\"parse_seconds_sum\": %.3f, \"gpu_call_seconds_sum\": %.3f, \"format_seconds_sum\": %.3f}\n",
                total_cols, wall, total_cols / wall, threads, gpus, t_scan, t_parse, t_gpu, t_format);
+    if (dev_timing)
+        printf("{\"ms_pack\": %.2f, \"ms_hash\": %.2f, \"ms_dedup\": %.2f, \"ms_prune\": %.2f, \"ms_scatter\": %.2f, \"ms_bls\": %.2f, \"windows\": %" PRId64
+               ", \"unique\": %" PRId64 "}\n", dev_ms[0], dev_ms[1], dev_ms[2], dev_ms[3], dev_ms[4], dev_ms[5], dev_windows, dev_unique);
     // species of the model never seen in any alignment (build_tracks.hpp:487-504)
     for (int s = 0; s < nl; ++s) {
         bool any = false;

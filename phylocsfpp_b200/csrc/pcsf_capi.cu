@@ -58,6 +58,7 @@ struct DevBuf {
 struct pcsf_model {
     int device = 0;
     int sm_count = 148;
+    cudaStream_t own_stream = nullptr;   // the host-buffer entry points run here (non-blocking: handles on one GPU overlap)
     ModelHost host;
     // device blob
     double *d_pstream[2] = {nullptr, nullptr}, *d_leafPT[2] = {nullptr, nullptr};
@@ -173,6 +174,7 @@ extern "C" pcsf_status pcsf_model_create(const pcsf_model_desc *d, int device, p
     }
     CK(cudaMalloc(&m->d_bad, sizeof(int)));
     CK(cudaMemset(m->d_bad, 0, sizeof(int)));
+    if (!getenv("PCSF_LEGACY_STREAM")) CK(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
     CK(cudaMalloc(&m->d_nuniq, sizeof(uint32_t) * MAX_CHUNKS));
     for (auto &e : m->ev) CK(cudaEventCreate(&e));
     m->prune_nwarp = PR_MAX_NWARP;
@@ -210,6 +212,7 @@ extern "C" void pcsf_model_destroy(pcsf_model *m) {
     }
     cudaFree(m->d_program); cudaFree(m->d_bls_prog); cudaFree(m->d_bl); cudaFree(m->d_gemm_edges);
     cudaFree(m->d_bad); cudaFree(m->d_nuniq); cudaFree(m->d_tc5_steps); cudaFree(m->d_tc5_scratch);
+    if (m->own_stream) cudaStreamDestroy(m->own_stream);
     DevBuf *bufs[] = {&m->codes, &m->klo, &m->khi, &m->slot, &m->flag, &m->uniq, &m->pidx, &m->table, &m->slotmin,
                       &m->bsums, &m->logz, &m->anc, &m->misc, &m->io_in, &m->io_out, &m->perwin, &m->mle};
     for (DevBuf *b : bufs) b->release();
@@ -483,16 +486,17 @@ extern "C" pcsf_status pcsf_tracks_device_finish(pcsf_model *m, void *cuda_strea
     if (!m) return fail(PCSF_ERR_INVALID, "null model");
     CK(cudaSetDevice(m->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    CK(cudaStreamSynchronize(st));
     int bad = 0;
-    CK(cudaMemcpy(&bad, m->d_bad, sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpyAsync(&bad, m->d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     m->last.n_windows = m->last_nwin;
     m->last.n_chunks = m->last_chunks;
     m->last.n_launches = m->launches;
     m->last.n_unique = 0;
     if (m->last_chunks > 0) {
         std::vector<uint32_t> nu(m->last_chunks);
-        CK(cudaMemcpy(nu.data(), m->d_nuniq, sizeof(uint32_t) * m->last_chunks, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpyAsync(nu.data(), m->d_nuniq, sizeof(uint32_t) * m->last_chunks, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
         for (uint32_t v : nu) m->last.n_unique += v;
     }
     if (stats) *stats = m->last;
@@ -512,20 +516,21 @@ extern "C" pcsf_status pcsf_tracks(pcsf_model *m, const uint8_t *seqs, int64_t L
     CK(m->io_in.reserve((size_t)ldd * nl));
     const size_t out_bytes = (size_t)W * 16 + (size_t)L * 8 + (pattern_index ? (size_t)W * 8 : 0) + 64;
     CK(m->io_out.reserve(out_bytes));
-    CK(cudaMemcpy2D(m->io_in.p, (size_t)ldd, seqs, (size_t)ld, (size_t)L, (size_t)nl, cudaMemcpyHostToDevice));
+    // everything on the handle's own non-blocking stream: the copies of one handle overlap the kernels of another on the same GPU, and
+    // with pinned host buffers (pcsf_alloc_pinned) they are plain DMA
+    cudaStream_t st = m->own_stream;
+    CK(cudaMemcpy2DAsync(m->io_in.p, (size_t)ldd, seqs, (size_t)ld, (size_t)L, (size_t)nl, cudaMemcpyHostToDevice, st));
     double *d_plus = m->io_out.as<double>(), *d_minus = d_plus + W, *d_bls = d_minus + W;
     uint32_t *d_pat = pattern_index ? reinterpret_cast<uint32_t *>(d_bls + L) : nullptr;
-    pcsf_status rc = pcsf_tracks_device(m, m->io_in.as<uint8_t>(), L, ldd, flags, d_plus, d_minus, d_bls, d_pat, nullptr);
-    if (rc) return rc;
-    rc = pcsf_tracks_device_finish(m, nullptr, stats);
+    pcsf_status rc = pcsf_tracks_device(m, m->io_in.as<uint8_t>(), L, ldd, flags, d_plus, d_minus, d_bls, d_pat, st);
     if (rc) return rc;
     if ((flags & PCSF_TRACKS_SCORES) && W > 0) {
-        CK(cudaMemcpy(plus, d_plus, (size_t)W * 8, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(minus, d_minus, (size_t)W * 8, cudaMemcpyDeviceToHost));
-        if (pattern_index) CK(cudaMemcpy(pattern_index, d_pat, (size_t)W * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpyAsync(plus, d_plus, (size_t)W * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(minus, d_minus, (size_t)W * 8, cudaMemcpyDeviceToHost, st));
+        if (pattern_index) CK(cudaMemcpyAsync(pattern_index, d_pat, (size_t)W * 8, cudaMemcpyDeviceToHost, st));
     }
-    if (flags & PCSF_TRACKS_BLS) CK(cudaMemcpy(bls, d_bls, (size_t)L * 8, cudaMemcpyDeviceToHost));
-    return PCSF_OK;
+    if (flags & PCSF_TRACKS_BLS) CK(cudaMemcpyAsync(bls, d_bls, (size_t)L * 8, cudaMemcpyDeviceToHost, st));
+    return pcsf_tracks_device_finish(m, st, stats);
 }
 
 extern "C" void *pcsf_alloc_pinned(size_t bytes) {
@@ -545,7 +550,7 @@ extern "C" pcsf_status pcsf_score_msa(pcsf_model *m, pcsf_strategy strategy, int
     CK(cudaSetDevice(m->device));
     if (n_aln == 0) return PCSF_OK;
     const int nl = m->host.nl;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = m->own_stream;
     // concatenate the alignments along the columns into one [nl][Ltot] matrix (2 pad columns between them)
     std::vector<int64_t> col_start(n_aln), win_start(n_aln), lens(len, len + n_aln);
     int64_t Ltot = 0, nwin = 0;

@@ -180,7 +180,7 @@ int main_build_tracks(int argc, char **argv) {
         // chains are computed and ignored): keeps the per-call cost off the many short chains of a gappy file
         std::vector<std::pair<size_t, size_t>> groups;
         {
-            const int64_t GROUP_COLS = getenv("PCSF_HOST_GROUP_COLS") ? atoll(getenv("PCSF_HOST_GROUP_COLS")) : (1 << 20);
+            const int64_t GROUP_COLS = getenv("PCSF_HOST_GROUP_COLS") ? atoll(getenv("PCSF_HOST_GROUP_COLS")) : (1 << 19);          // 512 Ki: three or more groups per worker on chromosome-sized files (1 Mi left a partial last round)
             size_t g0 = 0;
             int64_t acc = 0;
             for (size_t ci = 0; ci < chains.size(); ++ci) {

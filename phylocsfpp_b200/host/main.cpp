@@ -414,7 +414,9 @@ int main_score_msa(int argc, char **argv) {
         t_scan += since(s0);
         warn_unresolved(maf);
         const std::vector<MafFile::Chain> &chains = maf.chains();
-        const size_t BATCH = 4096;
+        // alignments per library call (measured on 100 k config-5 alignments, MLE: 4096 ... 131072 per call all take 5.3-5.7 s — the GPU
+        // is bound by the evaluations themselves, not by the tail of a call)
+        const size_t BATCH = getenv("PCSF_HOST_MSA_BATCH") ? (size_t)atoll(getenv("PCSF_HOST_MSA_BATCH")) : 4096;
         const size_t nbatch = (chains.size() + BATCH - 1) / BATCH;
         OrderedSink sink;
         sink.resize(nbatch);

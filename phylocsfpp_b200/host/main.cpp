@@ -156,46 +156,49 @@ int main_build_tracks(int argc, char **argv) {
     double t_gpu = 0.0;
     const auto t_start = std::chrono::steady_clock::now();
 
+    // All input files are scanned first and their chain groups go into ONE work queue: the workers never wait at a file boundary
+    // (chromosome-sized files used to end with a partially filled round of workers each); the writer still emits file after file.
+    struct FileCtx { std::string path, out_dir; std::unique_ptr<MafFile> maf; size_t chain0 = 0; };
+    struct Group { int file; size_t c0, c1; };
+    std::vector<FileCtx> fctx;
+    std::vector<Group> groups;
+    size_t total_chains = 0;
     for (size_t fi = 1; fi < a.pos.size(); ++fi) {
-        const std::string &path = a.pos[fi];
-        std::string out_dir = a.str("output");
-        if (out_dir.empty()) {
-            const size_t p = path.find_last_of('/');
-            out_dir = p == std::string::npos ? "./" : path.substr(0, p);
+        FileCtx fc;
+        fc.path = a.pos[fi];
+        fc.out_dir = a.str("output");
+        if (fc.out_dir.empty()) {
+            const size_t p = fc.path.find_last_of('/');
+            fc.out_dir = p == std::string::npos ? "./" : fc.path.substr(0, p);
         } else {
-            create_directory(out_dir);
+            create_directory(fc.out_dir);
         }
         const auto s0 = std::chrono::steady_clock::now();
-        MafFile maf(path, model, true, threads);
+        fc.maf.reset(new MafFile(fc.path, model, true, threads));
         t_scan += std::chrono::duration<double>(std::chrono::steady_clock::now() - s0).count();
-        warn_unresolved(maf);
-        const std::vector<MafFile::Chain> &chains = maf.chains();
-        FILE *files[7];
-        const char *mode = fi > 1 ? "a" : "w";
-        files[0] = fopen((out_dir + "/PhyloCSFpower.wig").c_str(), mode);
-        for (int k = 0; k < 6; ++k) files[1 + k] = raw ? fopen((out_dir + "/PhyloCSFRaw" + kFrames[k] + ".wig").c_str(), mode) : nullptr;
-        if (!files[0] || (raw && !files[1])) die("Error creating output files in '%s'!", out_dir.c_str());
-
+        warn_unresolved(*fc.maf);
+        fc.chain0 = total_chains;
+        const std::vector<MafFile::Chain> &chains = fc.maf->chains();
         // consecutive chains are scored in one library call (their columns concatenated; the windows that straddle two
         // chains are computed and ignored): keeps the per-call cost off the many short chains of a gappy file
-        std::vector<std::pair<size_t, size_t>> groups;
-        {
-            const int64_t GROUP_COLS = getenv("PCSF_HOST_GROUP_COLS") ? atoll(getenv("PCSF_HOST_GROUP_COLS")) : (1 << 19);          // 512 Ki: three or more groups per worker on chromosome-sized files (1 Mi left a partial last round)
-            size_t g0 = 0;
-            int64_t acc = 0;
-            for (size_t ci = 0; ci < chains.size(); ++ci) {
-                acc += chains[ci].ref_cols + 2;
-                if (acc >= GROUP_COLS || ci + 1 == chains.size() || ci + 1 - g0 >= 4096) { groups.emplace_back(g0, ci + 1); g0 = ci + 1; acc = 0; }
-            }
+        const int64_t GROUP_COLS = getenv("PCSF_HOST_GROUP_COLS") ? atoll(getenv("PCSF_HOST_GROUP_COLS")) : (1 << 19);
+        size_t g0 = 0;
+        int64_t acc = 0;
+        for (size_t ci = 0; ci < chains.size(); ++ci) {
+            acc += chains[ci].ref_cols + 2;
+            if (acc >= GROUP_COLS || ci + 1 == chains.size() || ci + 1 - g0 >= 4096) { groups.push_back(Group{(int)fctx.size(), g0, ci + 1}); g0 = ci + 1; acc = 0; }
         }
-        OrderedSink sink;
-        sink.resize(chains.size());
-        std::atomic<size_t> next{0};
-        std::atomic<int64_t> cols{0};
-        std::mutex gpu_time_mu;
-        std::vector<std::thread> workers;
-        for (int t = 0; t < threads; ++t)
-            workers.emplace_back([&, t] {
+        total_chains += chains.size();
+        fctx.push_back(std::move(fc));
+    }
+    OrderedSink sink;
+    sink.resize(total_chains);
+    std::atomic<size_t> next{0};
+    std::atomic<int64_t> cols{0};
+    std::mutex gpu_time_mu;
+    std::vector<std::thread> workers;
+    for (int t = 0; t < threads; ++t)
+        workers.emplace_back([&, t] {
                 std::vector<Alignment> alns;
                 std::vector<uint8_t> mat;
                 std::vector<double> plus, minus, bls;
@@ -204,7 +207,10 @@ int main_build_tracks(int argc, char **argv) {
                 auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
                 for (size_t gi = next++; gi < groups.size(); gi = next++) {
                     const auto p0 = now();
-                    const size_t c0 = groups[gi].first, c1 = groups[gi].second;
+                    const Group &grp = groups[gi];
+                    MafFile &maf = *fctx[grp.file].maf;
+                    const std::vector<MafFile::Chain> &chains = maf.chains();
+                    const size_t c0 = grp.c0, c1 = grp.c1, chain0 = fctx[grp.file].chain0;
                     alns.resize(c1 - c0);
                     int64_t Ltot = 0;
                     std::vector<int64_t> col0(c1 - c0);
@@ -291,28 +297,35 @@ int main_build_tracks(int argc, char **argv) {
                                 }
                             }
                         }
-                        sink.put(ci, std::move(text));
+                        sink.put(chain0 + ci, std::move(text));
                     }
                     my_fmt += secs(f0, now());
                 }
                 std::lock_guard<std::mutex> g(gpu_time_mu);
                 t_gpu += my_gpu; t_parse += my_parse; t_format += my_fmt;
-            });
+        });
+    for (size_t fi = 0; fi < fctx.size(); ++fi) {
+        const std::string &out_dir = fctx[fi].out_dir;
+        MafFile &maf = *fctx[fi].maf;
+        const std::vector<MafFile::Chain> &chains = maf.chains();
+        FILE *files[7];
+        const char *mode = fi > 0 ? "a" : "w";          // build_tracks.hpp:245-259: later files append
+        files[0] = fopen((out_dir + "/PhyloCSFpower.wig").c_str(), mode);
+        for (int k = 0; k < 6; ++k) files[1 + k] = raw ? fopen((out_dir + "/PhyloCSFRaw" + kFrames[k] + ".wig").c_str(), mode) : nullptr;
+        if (!files[0] || (raw && !files[1])) die("Error creating output files in '%s'!", out_dir.c_str());
         size_t bytes_done = 0;
         for (size_t ci = 0; ci < chains.size(); ++ci) {
-            std::vector<std::string> text = sink.take(ci);
+            std::vector<std::string> text = sink.take(fctx[fi].chain0 + ci);
             for (int k = 0; k < 7; ++k) if (files[k] && !text[k].empty()) fwrite(text[k].data(), 1, text[k].size(), files[k]);
             bytes_done += maf.chain_bytes(chains[ci]);
             if ((ci & 15) == 0 || ci + 1 == chains.size()) {
                 printf("\33[2K\r");
-                if (a.pos.size() > 2) printf("File %zu of %zu: ", fi, a.pos.size() - 1);
+                if (fctx.size() > 1) printf("File %zu of %zu: ", fi + 1, fctx.size());
                 printf("%.2f / %.2f MB (%3.2f %%)\r", bytes_done / 1048576.0, maf.file_size() / 1048576.0, 100.0 * bytes_done / std::max<size_t>(1, maf.file_size()));
                 fflush(stdout);
             }
         }
-        for (auto &w : workers) w.join();
         for (FILE *f : files) if (f) fclose(f);
-        total_cols += cols;
         // PhyloCSF-HMM over the text of the six raw tracks (build_tracks.hpp:262-348), one thread per track
         if (smooth || regions) {
             printf("\33[2K\rSmoothing scores and/or computing coding-regions ...\r");
@@ -332,6 +345,8 @@ int main_build_tracks(int argc, char **argv) {
             for (auto &t : sm) t.join();
         }
     }
+    for (auto &w : workers) w.join();
+    total_cols += cols;
     const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
     printf("\nDone!\n");
     if (getenv("PCSF_HOST_STATS"))

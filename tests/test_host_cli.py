@@ -198,3 +198,27 @@ def test_score_msa_cli_golden(golden_dir, tmp_path):
     for o, g in zip(ours, gold):
         assert o[:4] == g[:4] and o[6] == g[6]
         assert abs(float(o[4]) - float(g[4])) <= 1e-3 and abs(float(o[5]) - float(g[5])) <= 1e-3
+
+
+@pytest.mark.gpu
+def test_build_tracks_cli_multiple_files(golden_dir, tmp_path):
+    """Several alignment files in one call (one work queue across the files, the writer emits file after file): every output is the
+    concatenation of the single-file outputs, as with the reference's append mode for file_id > 1 (build_tracks.hpp:245-259)."""
+    _need_bin()
+    R = os.path.join(golden_dir, "ref-generated")
+    m1 = _gunzip(os.path.join(R, "tracks12.maf.gz"), str(tmp_path))
+    m2 = os.path.join(str(tmp_path), "second.maf")
+    with open(m1) as fi, open(m2, "w") as fo:
+        fo.write(fi.read().replace(".chr1 ", ".chr2 "))
+    names = ["PhyloCSFpower.wig"] + [f"PhyloCSFRaw{s}{f}.wig" for s in "+-" for f in (1, 2, 3)]
+    outs = {}
+    for tag, files in (("a", [m1]), ("b", [m2]), ("ab", [m1, m2])):
+        out = os.path.join(str(tmp_path), "o_" + tag)
+        subprocess.run([BIN, "build-tracks", "--threads", "5", "--output", out, "12flies"] + files, check=True, capture_output=True)
+        outs[tag] = out
+    for n in names:
+        a = open(os.path.join(outs["a"], n), "rb").read()
+        b = open(os.path.join(outs["b"], n), "rb").read()
+        ab = open(os.path.join(outs["ab"], n), "rb").read()
+        assert ab == a + b, n
+        assert a == gzip.open(os.path.join(R, "tracks12." + n + ".gz"), "rb").read(), n

@@ -21,16 +21,16 @@ namespace pcsf {
 __constant__ uint8_t c_dna_lut[256];
 
 // ---------------------------------------------------------------------------------------------------
-// k_pack: codes[s][i] = get_dna_id(seqs[s][i]); columns [L, ld_out) are filled with 4 ("N").
+// k_pack: codes[s][i] = get_dna_id(seqs[s][i]); columns [L, cols_out) are filled with 4 ("N").
 // 16 bytes per thread when rows are 16-byte aligned, scalar otherwise.
 __global__ void k_pack(const uint8_t *__restrict__ seqs, int64_t L, int64_t ld_in, int nl,
-                       uint8_t *__restrict__ codes, int64_t ld_out, int *__restrict__ bad) {
+                       uint8_t *__restrict__ codes, int64_t ld_out, int64_t cols_out, int *__restrict__ bad) {
     const int s = blockIdx.y;
     const uint8_t *src = seqs + (int64_t)s * ld_in;
-    uint8_t *dst = codes + (int64_t)s * ld_out;
+    uint8_t *dst = codes + (int64_t)s * ld_out;          // ld_out: row stride; cols_out: columns written (>= L, a multiple of 16)
     const bool vec = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
     int local_bad = 0;
-    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16; i < ld_out;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16; i < cols_out;
          i += (int64_t)gridDim.x * blockDim.x * 16) {
         uint32_t out[4];
         if (vec && i + 16 <= L) {

@@ -59,6 +59,15 @@ struct pcsf_model {
     int device = 0;
     int sm_count = 148;
     cudaStream_t own_stream = nullptr;   // the host-buffer entry points run here (non-blocking: handles on one GPU overlap)
+    cudaStream_t copy_stream = nullptr;  // results of a finished dedup chunk go home while the next chunk is pruned
+    cudaEvent_t ev_chunk = nullptr;
+    // host destinations of the call in flight (pcsf_tracks only; null for the device-pointer entry point)
+    double *h_plus = nullptr, *h_minus = nullptr, *h_bls = nullptr;
+    uint32_t *h_pat = nullptr;
+    const uint8_t *h_seqs = nullptr;     // non-null: the input is still on the host and arrives segment by segment (one per dedup chunk)
+    int64_t h_ld = 0;
+    cudaStream_t h2d_stream = nullptr;
+    std::vector<cudaEvent_t> ev_h2d;
     ModelHost host;
     // device blob
     double *d_pstream[2] = {nullptr, nullptr}, *d_leafPT[2] = {nullptr, nullptr};
@@ -174,7 +183,12 @@ extern "C" pcsf_status pcsf_model_create(const pcsf_model_desc *d, int device, p
     }
     CK(cudaMalloc(&m->d_bad, sizeof(int)));
     CK(cudaMemset(m->d_bad, 0, sizeof(int)));
-    if (!getenv("PCSF_LEGACY_STREAM")) CK(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
+    if (!getenv("PCSF_LEGACY_STREAM")) {
+        CK(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&m->h2d_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&m->ev_chunk, cudaEventDisableTiming));
+    }
     CK(cudaMalloc(&m->d_nuniq, sizeof(uint32_t) * MAX_CHUNKS));
     for (auto &e : m->ev) CK(cudaEventCreate(&e));
     m->prune_nwarp = PR_MAX_NWARP;
@@ -213,6 +227,10 @@ extern "C" void pcsf_model_destroy(pcsf_model *m) {
     cudaFree(m->d_program); cudaFree(m->d_bls_prog); cudaFree(m->d_bl); cudaFree(m->d_gemm_edges);
     cudaFree(m->d_bad); cudaFree(m->d_nuniq); cudaFree(m->d_tc5_steps); cudaFree(m->d_tc5_scratch);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
+    if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+    if (m->h2d_stream) cudaStreamDestroy(m->h2d_stream);
+    for (cudaEvent_t e : m->ev_h2d) cudaEventDestroy(e);
+    if (m->ev_chunk) cudaEventDestroy(m->ev_chunk);
     DevBuf *bufs[] = {&m->codes, &m->klo, &m->khi, &m->slot, &m->flag, &m->uniq, &m->pidx, &m->table, &m->slotmin,
                       &m->bsums, &m->logz, &m->anc, &m->misc, &m->io_in, &m->io_out, &m->perwin, &m->mle};
     for (DevBuf *b : bufs) b->release();
@@ -410,7 +428,7 @@ static pcsf_status run_pack(pcsf_model *m, const uint8_t *d_seqs, int64_t L, int
     CK(cudaMemsetAsync(m->d_bad, 0, sizeof(int), st));
     const int64_t nvec = m->codes_ld / 16;
     dim3 grid((unsigned)std::min<int64_t>((nvec + 255) / 256, 65535), nl);
-    m->launches++; k_pack<<<grid, 256, 0, st>>>(d_seqs, L, ld, nl, m->codes.as<uint8_t>(), m->codes_ld, m->d_bad);
+    m->launches++; k_pack<<<grid, 256, 0, st>>>(d_seqs, L, ld, nl, m->codes.as<uint8_t>(), m->codes_ld, m->codes_ld, m->d_bad);
     CK(cudaGetLastError());
     return PCSF_OK;
 }
@@ -421,6 +439,25 @@ static pcsf_status run_bls(pcsf_model *m, int64_t L, int raw, double *d_out, cud
     m->launches++; k_bls<<<(unsigned)((L + BLS_THREADS - 1) / BLS_THREADS), BLS_THREADS, sh, st>>>(
         m->codes.as<uint8_t>(), m->codes_ld, m->host.nl, L, m->d_bls_prog, (int)m->host.bls_prog.size(),
         m->host.bls_depth, m->host.bls_all, raw, d_out);
+    CK(cudaGetLastError());
+    return PCSF_OK;
+}
+
+// Columns [s0, s1) only (s0 a multiple of 16): the pieces of run_pack / run_bls for an input that arrives in segments.
+static pcsf_status run_pack_segment(pcsf_model *m, const uint8_t *d_seqs, int64_t ld, int64_t s0, int64_t s1, bool last, cudaStream_t st) {
+    const int nl = m->host.nl;
+    const int64_t out_cols = last ? m->codes_ld - s0 : s1 - s0;
+    dim3 grid((unsigned)std::min<int64_t>((out_cols / 16 + 255) / 256 + 1, 65535), nl);
+    m->launches++; k_pack<<<grid, 256, 0, st>>>(d_seqs + s0, s1 - s0, ld, nl, m->codes.as<uint8_t>() + s0, m->codes_ld, out_cols, m->d_bad);
+    CK(cudaGetLastError());
+    return PCSF_OK;
+}
+static pcsf_status run_bls_segment(pcsf_model *m, int64_t s0, int64_t s1, double *d_out, cudaStream_t st) {
+    if (s1 <= s0) return PCSF_OK;
+    const size_t sh = (size_t)std::max(1, m->host.bls_depth) * BLS_THREADS * 8;
+    m->launches++; k_bls<<<(unsigned)((s1 - s0 + BLS_THREADS - 1) / BLS_THREADS), BLS_THREADS, sh, st>>>(
+        m->codes.as<uint8_t>() + s0, m->codes_ld, m->host.nl, s1 - s0, m->d_bls_prog, (int)m->host.bls_prog.size(),
+        m->host.bls_depth, m->host.bls_all, 0, d_out + s0);
     CK(cudaGetLastError());
     return PCSF_OK;
 }
@@ -441,11 +478,45 @@ extern "C" pcsf_status pcsf_tracks_device(pcsf_model *m, const uint8_t *d_seqs, 
     m->launches = 0;
     if (L == 0) return PCSF_OK;
     pcsf_status rc;
+    // Segmented input (pcsf_tracks with two or more dedup chunks): d_seqs is the device staging buffer that the h2d stream fills
+    // segment by segment from the caller's host matrix; every chunk packs (and BLS-scores) its own segment right before it is keyed
+    // and pruned, so the copy of segment c+1 runs under the pruning of chunk c.  Segment c = columns [s0, s1): s1 = the chunk's last
+    // window + 2 columns of halo, rounded up to 16; the last one ends at L and also writes the padding.
+    const bool seg = m->h_seqs != nullptr;
+    const int64_t W_all = L - 2;
+    const int64_t nchunks_all = W_all > 0 ? (W_all + m->chunk_cols - 1) / m->chunk_cols : 0;
+    auto seg_end = [&](int64_t c) {
+        if (c + 1 >= nchunks_all) return L;
+        const int64_t c1 = std::min(W_all, (c + 1) * m->chunk_cols);
+        return std::min<int64_t>(L, ((c1 + 2 + 15) / 16) * 16);
+    };
+    if (seg) {
+        m->codes_ld = ((L + 16 + 15) / 16) * 16;
+        CK(m->codes.reserve((size_t)m->codes_ld * m->host.nl));
+        CK(cudaMemsetAsync(m->d_bad, 0, sizeof(int), st));
+        while ((int64_t)m->ev_h2d.size() < nchunks_all) {
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            m->ev_h2d.push_back(e);
+        }
+        for (int64_t c = 0; c < nchunks_all; ++c) {
+            const int64_t s0 = c == 0 ? 0 : seg_end(c - 1), s1 = seg_end(c);
+            if (s1 > s0)
+                CK(cudaMemcpy2DAsync(const_cast<uint8_t *>(d_seqs) + s0, (size_t)ld, m->h_seqs + s0, (size_t)m->h_ld, (size_t)(s1 - s0),
+                                     (size_t)m->host.nl, cudaMemcpyHostToDevice, m->h2d_stream));
+            CK(cudaEventRecord(m->ev_h2d[c], m->h2d_stream));
+        }
+    }
     if (m->timing) CK(cudaEventRecord(m->ev[4], st));
-    if ((rc = run_pack(m, d_seqs, L, ld, st))) return rc;
+    if (!seg && (rc = run_pack(m, d_seqs, L, ld, st))) return rc;
     if (m->timing) CK(cudaEventRecord(m->ev[5], st));
-    if (flags & PCSF_TRACKS_BLS) {
+    if ((flags & PCSF_TRACKS_BLS) && !seg) {
         if ((rc = run_bls(m, L, 0, d_bls, st))) return rc;
+        if (m->h_bls && m->copy_stream) {          // host-buffer call: the BLS vector goes home under the pruning
+            CK(cudaEventRecord(m->ev_chunk, st));
+            CK(cudaStreamWaitEvent(m->copy_stream, m->ev_chunk, 0));
+            CK(cudaMemcpyAsync(m->h_bls, d_bls, (size_t)L * 8, cudaMemcpyDeviceToHost, m->copy_stream));
+        }
     }
     if (m->timing) {
         CK(cudaEventRecord(m->ev[6], st));
@@ -460,6 +531,21 @@ extern "C" pcsf_status pcsf_tracks_device(pcsf_model *m, const uint8_t *d_seqs, 
         for (int64_t c = 0; c < nchunks; ++c) {
             const int64_t c0 = c * m->chunk_cols, c1 = std::min(W, c0 + m->chunk_cols);
             const uint32_t nwin = (uint32_t)(2 * (c1 - c0));
+            if (seg) {
+                const int64_t s0 = c == 0 ? 0 : seg_end(c - 1), s1 = seg_end(c);
+                CK(cudaStreamWaitEvent(st, m->ev_h2d[c], 0));
+                if (s1 > s0 || s1 == L) {
+                    if (s1 > s0 || c + 1 == nchunks) { if ((rc = run_pack_segment(m, d_seqs, ld, s0, s1, s1 == L, st))) return rc; }
+                    if ((flags & PCSF_TRACKS_BLS) && s1 > s0) {
+                        if ((rc = run_bls_segment(m, s0, s1, d_bls, st))) return rc;
+                        if (m->h_bls) {
+                            CK(cudaEventRecord(m->ev_chunk, st));
+                            CK(cudaStreamWaitEvent(m->copy_stream, m->ev_chunk, 0));
+                            CK(cudaMemcpyAsync(m->h_bls + s0, d_bls + s0, (size_t)(s1 - s0) * 8, cudaMemcpyDeviceToHost, m->copy_stream));
+                        }
+                    }
+                }
+            }
             WinSpace ws{m->codes.as<uint8_t>(), m->codes_ld, m->host.nl, 0, c0, nullptr};
             if ((rc = dedup_and_prune(m, ws, nwin, !(flags & PCSF_TRACKS_NO_DEDUP), false, (flags & PCSF_TRACKS_TC5) ? 2 : (flags & PCSF_TRACKS_FP32) ? 1 : 0, m->d_nuniq + c, d_pattern_index,
                                       2 * c0, st, &m->last.ms_hash, &m->last.ms_dedup, &m->last.ms_prune)))
@@ -474,6 +560,14 @@ extern "C" pcsf_status pcsf_tracks_device(pcsf_model *m, const uint8_t *d_seqs, 
                 float t;
                 CK(cudaEventElapsedTime(&t, m->ev[0], m->ev[1]));
                 m->last.ms_scatter += t;
+            }
+            if (m->h_plus && m->copy_stream) {          // host-buffer call: this chunk's scores go home while the next one is pruned
+                CK(cudaEventRecord(m->ev_chunk, st));
+                CK(cudaStreamWaitEvent(m->copy_stream, m->ev_chunk, 0));
+                CK(cudaMemcpyAsync(m->h_plus + c0, d_plus + c0, (size_t)(c1 - c0) * 8, cudaMemcpyDeviceToHost, m->copy_stream));
+                CK(cudaMemcpyAsync(m->h_minus + c0, d_minus + c0, (size_t)(c1 - c0) * 8, cudaMemcpyDeviceToHost, m->copy_stream));
+                if (m->h_pat && d_pattern_index)
+                    CK(cudaMemcpyAsync(m->h_pat + 2 * c0, d_pattern_index + 2 * c0, (size_t)(c1 - c0) * 8, cudaMemcpyDeviceToHost, m->copy_stream));
             }
         }
         m->last_chunks = (int)nchunks;
@@ -519,18 +613,34 @@ extern "C" pcsf_status pcsf_tracks(pcsf_model *m, const uint8_t *seqs, int64_t L
     // everything on the handle's own non-blocking stream: the copies of one handle overlap the kernels of another on the same GPU, and
     // with pinned host buffers (pcsf_alloc_pinned) they are plain DMA
     cudaStream_t st = m->own_stream;
-    CK(cudaMemcpy2DAsync(m->io_in.p, (size_t)ldd, seqs, (size_t)ld, (size_t)L, (size_t)nl, cudaMemcpyHostToDevice, st));
+    const int64_t nchunks = W > 0 ? (W + m->chunk_cols - 1) / m->chunk_cols : 0;
+    const bool segmented = m->copy_stream != nullptr && !m->timing && (flags & PCSF_TRACKS_SCORES) && nchunks >= 2 && nchunks <= MAX_CHUNKS;
+    if (!segmented) CK(cudaMemcpy2DAsync(m->io_in.p, (size_t)ldd, seqs, (size_t)ld, (size_t)L, (size_t)nl, cudaMemcpyHostToDevice, st));
+    m->h_seqs = segmented ? seqs : nullptr;
+    m->h_ld = ld;
     double *d_plus = m->io_out.as<double>(), *d_minus = d_plus + W, *d_bls = d_minus + W;
     uint32_t *d_pat = pattern_index ? reinterpret_cast<uint32_t *>(d_bls + L) : nullptr;
+    const bool piped = m->copy_stream != nullptr;
+    m->h_plus = ((flags & PCSF_TRACKS_SCORES) && W > 0 && piped) ? plus : nullptr;
+    m->h_minus = m->h_plus ? minus : nullptr;
+    m->h_pat = m->h_plus ? pattern_index : nullptr;
+    m->h_bls = ((flags & PCSF_TRACKS_BLS) && piped) ? bls : nullptr;
     pcsf_status rc = pcsf_tracks_device(m, m->io_in.as<uint8_t>(), L, ldd, flags, d_plus, d_minus, d_bls, d_pat, st);
-    if (rc) return rc;
-    if ((flags & PCSF_TRACKS_SCORES) && W > 0) {
-        CK(cudaMemcpyAsync(plus, d_plus, (size_t)W * 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(minus, d_minus, (size_t)W * 8, cudaMemcpyDeviceToHost, st));
-        if (pattern_index) CK(cudaMemcpyAsync(pattern_index, d_pat, (size_t)W * 8, cudaMemcpyDeviceToHost, st));
+    m->h_plus = m->h_minus = m->h_bls = nullptr;
+    m->h_pat = nullptr;
+    m->h_seqs = nullptr;
+    if (rc) { if (piped) { cudaStreamSynchronize(m->h2d_stream); cudaStreamSynchronize(m->copy_stream); } return rc; }
+    if (!piped) {
+        if ((flags & PCSF_TRACKS_SCORES) && W > 0) {
+            CK(cudaMemcpyAsync(plus, d_plus, (size_t)W * 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(minus, d_minus, (size_t)W * 8, cudaMemcpyDeviceToHost, st));
+            if (pattern_index) CK(cudaMemcpyAsync(pattern_index, d_pat, (size_t)W * 8, cudaMemcpyDeviceToHost, st));
+        }
+        if (flags & PCSF_TRACKS_BLS) CK(cudaMemcpyAsync(bls, d_bls, (size_t)L * 8, cudaMemcpyDeviceToHost, st));
     }
-    if (flags & PCSF_TRACKS_BLS) CK(cudaMemcpyAsync(bls, d_bls, (size_t)L * 8, cudaMemcpyDeviceToHost, st));
-    return pcsf_tracks_device_finish(m, st, stats);
+    rc = pcsf_tracks_device_finish(m, st, stats);
+    if (piped && cudaStreamSynchronize(m->copy_stream) != cudaSuccess && rc == PCSF_OK) rc = fail(PCSF_ERR_CUDA, "copy stream failed");
+    return rc;
 }
 
 extern "C" void *pcsf_alloc_pinned(size_t bytes) {

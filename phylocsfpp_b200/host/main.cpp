@@ -159,10 +159,11 @@ int main_build_tracks(int argc, char **argv) {
     // All input files are scanned first and their chain groups go into ONE work queue: the workers never wait at a file boundary
     // (chromosome-sized files used to end with a partially filled round of workers each); the writer still emits file after file.
     struct FileCtx { std::string path, out_dir; std::unique_ptr<MafFile> maf; size_t chain0 = 0; };
-    struct Group { int file; size_t c0, c1; };
+    struct Group { int file; size_t c0, c1; int64_t col_begin; };          // col_begin: reference columns of all chains before this group
     std::vector<FileCtx> fctx;
     std::vector<Group> groups;
     size_t total_chains = 0;
+    int64_t cols_before = 0;
     for (size_t fi = 1; fi < a.pos.size(); ++fi) {
         FileCtx fc;
         fc.path = a.pos[fi];
@@ -186,7 +187,11 @@ int main_build_tracks(int argc, char **argv) {
         int64_t acc = 0;
         for (size_t ci = 0; ci < chains.size(); ++ci) {
             acc += chains[ci].ref_cols + 2;
-            if (acc >= GROUP_COLS || ci + 1 == chains.size() || ci + 1 - g0 >= 4096) { groups.push_back(Group{(int)fctx.size(), g0, ci + 1}); g0 = ci + 1; acc = 0; }
+            if (acc >= GROUP_COLS || ci + 1 == chains.size() || ci + 1 - g0 >= 4096) {
+                groups.push_back(Group{(int)fctx.size(), g0, ci + 1, cols_before});
+                cols_before += acc;
+                g0 = ci + 1; acc = 0;
+            }
         }
         total_chains += chains.size();
         fctx.push_back(std::move(fc));
@@ -196,6 +201,12 @@ int main_build_tracks(int argc, char **argv) {
     std::atomic<size_t> next{0};
     std::atomic<int64_t> cols{0};
     std::mutex gpu_time_mu;
+    // back-pressure: the workers run at most this many reference columns ahead of the writer (their finished text waits in memory,
+    // about 16 bytes per column for the seven files)
+    const int64_t AHEAD_COLS = (int64_t)64 << 20;
+    std::mutex written_mu;
+    std::condition_variable written_cv;
+    int64_t written_cols = 0;
     std::vector<std::thread> workers;
     for (int t = 0; t < threads; ++t)
         workers.emplace_back([&, t] {
@@ -206,8 +217,12 @@ int main_build_tracks(int argc, char **argv) {
                 auto now = [] { return std::chrono::steady_clock::now(); };
                 auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
                 for (size_t gi = next++; gi < groups.size(); gi = next++) {
-                    const auto p0 = now();
                     const Group &grp = groups[gi];
+                    {
+                        std::unique_lock<std::mutex> g(written_mu);
+                        written_cv.wait(g, [&] { return grp.col_begin <= written_cols + AHEAD_COLS; });
+                    }
+                    const auto p0 = now();
                     MafFile &maf = *fctx[grp.file].maf;
                     const std::vector<MafFile::Chain> &chains = maf.chains();
                     const size_t c0 = grp.c0, c1 = grp.c1, chain0 = fctx[grp.file].chain0;
@@ -318,6 +333,8 @@ int main_build_tracks(int argc, char **argv) {
             std::vector<std::string> text = sink.take(fctx[fi].chain0 + ci);
             for (int k = 0; k < 7; ++k) if (files[k] && !text[k].empty()) fwrite(text[k].data(), 1, text[k].size(), files[k]);
             bytes_done += maf.chain_bytes(chains[ci]);
+            { std::lock_guard<std::mutex> g(written_mu); written_cols += chains[ci].ref_cols + 2; }
+            written_cv.notify_all();
             if ((ci & 15) == 0 || ci + 1 == chains.size()) {
                 printf("\33[2K\r");
                 if (fctx.size() > 1) printf("File %zu of %zu: ", fi + 1, fctx.size());

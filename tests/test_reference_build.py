@@ -252,3 +252,89 @@ def test_tc5_half_variant_matches(golden_dir, tmp_path):
         b = open(os.path.join(outs[1], n)).read().split("\n")
         assert len(a) == len(b)
         assert sum(x != y for x, y in zip(a, b)) <= len(a) // 1000 + 1
+
+
+# ------------------------------------------------------------------------------------------------ 4. differential runs
+def _oracle_build_tracks(model_name, maf, threshold=0.1, species=""):
+    """The oracle + reader-mirror pipeline of build-tracks: dict file name -> list of lines."""
+    m = load_model(model_name, species) if species else load_model(model_name)
+    mc, mnc = orc.OracleModel(m.tree, m.S_c, m.f_c), orc.OracleModel(m.tree, m.S_nc, m.f_nc)
+    out = {tracks.wig_filename(s, f): [] for s, f in tracks.FRAMES}
+    out["PhyloCSFpower.wig"] = []
+    for a in MafReader(maf, m.seqid_to_phyloid, m.nl, True, warn=False):
+        if a.L == 0:
+            continue
+        plus, minus = orc.window_codons(a.seqs)
+        p, mi = orc.run_tracks(mc, mnc, plus), orc.run_tracks(mc, mnc, minus)
+        b = orc.bls(m.tree, a.seqs)[1]
+        out["PhyloCSFpower.wig"] += tracks.power_wig(a.chrom, a.start_pos, b)
+        for (s, f), lines in tracks.raw_wigs(a.chrom, a.start_pos, a.chrom_len, p, mi, b, threshold=threshold).items():
+            out[tracks.wig_filename(s, f)] += lines
+    return out
+
+
+@pytest.mark.parametrize("model_name,cols,seed,extra", [("7yeast", 2500, 21, []), ("20flies", 1800, 22, []),
+                                                        ("12flies", 2200, 23, ["--power-threshold", "1"]),
+                                                        ("12flies", 2200, 24, ["--power-threshold", "0.5"]),
+                                                        ("29mammals", 900, 25, ["--species", SPECIES29])])
+def test_differential_build_tracks_oracle_vs_reference_binary(tmp_path, model_name, cols, seed, extra):
+    """Fresh synthetic MAFs (holes, reference gaps, unknown species) through the reference binary and through the oracle + reader
+    mirror: byte-identical wig files.  Includes the --power-threshold quirk (read with get_bool, build_tracks.hpp:416-417: "1" gives 1.0,
+    anything else 0.0) and a --species reduction."""
+    _need_ref()
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    os.environ["PCSF_SYNTH_CPU"] = "1"
+    from make_synth_maf import write_synth_maf
+    maf = os.path.join(str(tmp_path), "d.maf")
+    write_synth_maf(maf, load_model(model_name), cols, seed=seed, mean_block=70, hole_p=1 / 15.0, ref_gap=0.03, alien_p=0.1)
+    out = os.path.join(str(tmp_path), "ref")
+    subprocess.run([REF, "build-tracks", "--threads", "4", "--output", out] + extra + [model_name, maf], check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    threshold = 0.1
+    species = ""
+    if "--power-threshold" in extra:
+        threshold = 1.0 if extra[extra.index("--power-threshold") + 1] in ("1", "true", "one") else 0.0
+    if "--species" in extra:
+        species = extra[extra.index("--species") + 1]
+    ours = _oracle_build_tracks(model_name, maf, threshold, species)
+    for n in WIGS:
+        ref_lines = open(os.path.join(out, n)).read().split("\n")
+        if ref_lines and ref_lines[-1] == "":
+            ref_lines.pop()
+        assert ours[n] == ref_lines, n
+
+
+@pytest.mark.parametrize("model_name,seed", [("7yeast", 31), ("12flies", 32)])
+def test_differential_score_msa_oracle_vs_reference_binary(tmp_path, model_name, seed):
+    """Single-block alignments through the reference binary (FIXED with the ancestral score, and MLE) and through the oracle."""
+    _need_ref()
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    os.environ["PCSF_SYNTH_CPU"] = "1"
+    from make_synth_maf import write_synth_maf
+    m = load_model(model_name)
+    maf = os.path.join(str(tmp_path), "b.maf")
+    write_synth_maf(maf, m, 2500, seed=seed, loguniform_blocks=(20, 300), alien_p=0.1)
+    alns = list(MafReader(maf, m.seqid_to_phyloid, m.nl, False, warn=False))
+    mc, mnc = orc.OracleModel(m.tree, m.S_c, m.f_c), orc.OracleModel(m.tree, m.S_nc, m.f_nc)
+    for strategy in ("fixed", "mle"):
+        out = os.path.join(str(tmp_path), "o_" + strategy)
+        subprocess.run([REF, "score-msa", "--threads", "4", "--strategy", strategy, "--comp-phylo", "1", "--comp-anc", "1", "--output", out, model_name, maf],
+                       check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        gold = _rows(os.path.join(out, "b.maf.scores"))
+        assert len(gold) == len(alns) >= 8
+        forked = 0
+        for a, g in zip(alns, gold):
+            assert [a.chrom, str(a.start_pos), str(a.start_pos + a.L - 1), a.strand] == g[:4]
+            assert "%.6f" % np.float32(orc.bls(m.tree, a.seqs, per_base=False)[0]) == g[6]
+            pep = orc.translate(a.seqs)
+            if strategy == "fixed":
+                s, anc = orc.run_fixed(mc, mnc, pep, True)
+                assert abs(float(s) - float(g[4])) <= 1e-3 and abs(float(anc) - float(g[5])) <= 1e-3
+            else:
+                s, anc, _ = orc.run_mle(mc, mnc, pep, True)
+                d = max(abs(float(s) - float(g[4])), abs(float(anc) - float(g[5])))
+                assert d ** 2 <= 0.001          # test/tests.sh:41
+                forked += d > 1e-3
+        assert forked <= 1

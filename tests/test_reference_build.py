@@ -338,3 +338,24 @@ def test_differential_score_msa_oracle_vs_reference_binary(tmp_path, model_name,
                 assert d ** 2 <= 0.001          # test/tests.sh:41
                 forked += d > 1e-3
         assert forked <= 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model_name,cols,seed,extra", [("20flies", 6000, 41, []), ("53birds", 4000, 42, ["--power-threshold", "1"]),
+                                                        ("29mammals", 5000, 43, ["--species", SPECIES29])])
+def test_differential_cli_vs_reference_binary(tmp_path, model_name, cols, seed, extra):
+    """The product's command line and the reference binary side by side on a fresh synthetic MAF (the binary travels to the GPU box
+    with the repository snapshot): seven wig files byte-identical on the FP64 path."""
+    _need_ref()
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    os.environ["PCSF_SYNTH_CPU"] = "1"
+    from make_synth_maf import write_synth_maf
+    maf = os.path.join(str(tmp_path), "d.maf")
+    write_synth_maf(maf, load_model(model_name), cols, seed=seed, mean_block=80, hole_p=1 / 20.0, ref_gap=0.03, alien_p=0.1)
+    ref_out, our_out = os.path.join(str(tmp_path), "ref"), os.path.join(str(tmp_path), "ours")
+    subprocess.run([REF, "build-tracks", "--threads", "8", "--output", ref_out] + extra + [model_name, maf], check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.run([BIN, "build-tracks", "--threads", "3", "--output", our_out] + extra + [model_name, maf], check=True, capture_output=True)
+    for n in WIGS:
+        assert open(os.path.join(our_out, n), "rb").read() == open(os.path.join(ref_out, n), "rb").read(), n

@@ -45,7 +45,12 @@ inline bool parse_s_line(const char *p, const char *e, SLine &s) {
         while (p < e && *p == ' ') ++p;
         if (p >= e) break;
         const char *q = p;
-        while (q < e && *q != ' ') ++q;
+        if (n == 6) {          // the sequence text: nearly the whole line, so let memchr find its end
+            const char *sp = (const char *)memchr(p, ' ', (size_t)(e - p));
+            q = sp ? sp : e;
+        } else {
+            while (q < e && *q != ' ') ++q;
+        }
         tok[n] = p; len[n] = (int)(q - p); ++n;
         p = q;
     }
@@ -123,6 +128,7 @@ public:
         aln.L = 0; aln.seqs.clear();
         if (c.ref_id < 0) return;
         std::vector<std::string> rows(nl);
+        for (std::string &r : rows) r.reserve((size_t)c.ref_cols + (size_t)c.ref_cols / 16 + 64);
         std::string key;
         for (size_t bi : c.blocks) {
             const BlockMeta &b = blocks_[bi];
@@ -154,18 +160,26 @@ public:
                 }
         }
         // delete the columns where the reference has '-' (:631-669), then cut at the breakpoint + 2
+        // (reference gaps are rare, so the kept columns are a few long runs: one memcpy per run and row instead of a byte gather)
         const std::string &ref = rows[c.ref_id];
-        std::vector<uint32_t> keep;
-        keep.reserve(ref.size());
-        for (size_t i = 0; i < ref.size(); ++i) if (ref[i] != '-') keep.push_back((uint32_t)i);
-        size_t L = keep.size();
-        if (c.keep_cols >= 0 && (size_t)c.keep_cols < L) L = (size_t)c.keep_cols;
+        std::vector<std::pair<size_t, size_t>> runs;          // [begin, end) of kept alignment columns
+        size_t kept = 0;
+        const size_t limit = c.keep_cols >= 0 ? (size_t)c.keep_cols : (size_t)-1;
+        for (size_t i = 0; i < ref.size() && kept < limit;) {
+            const char *gap = (const char *)memchr(ref.data() + i, '-', ref.size() - i);
+            size_t e = gap ? (size_t)(gap - ref.data()) : ref.size();
+            if (e - i > limit - kept) e = i + (limit - kept);
+            if (e > i) { runs.emplace_back(i, e); kept += e - i; }
+            i = e;
+            while (i < ref.size() && ref[i] == '-') ++i;
+        }
+        const size_t L = kept;
         aln.L = (int64_t)L;
         aln.seqs.resize((size_t)nl * L);
         for (int s = 0; s < nl; ++s) {
             const char *src = rows[s].data();
             uint8_t *dst = aln.seqs.data() + (size_t)s * L;
-            for (size_t i = 0; i < L; ++i) dst[i] = (uint8_t)src[keep[i]];
+            for (const auto &r : runs) { memcpy(dst, src + r.first, r.second - r.first); dst += r.second - r.first; }
         }
     }
 

@@ -549,7 +549,8 @@ int main_score_msa(int argc, char **argv) {
 // ------------------------------------------------------------------------------------- dump-alignments
 // Test hook (no GPU needed): what the reader hands to the likelihood core, one line per alignment.
 int main_dump_alignments(int argc, char **argv) {
-    const Args a = parse_args(argc, argv, {"concatenate", "threads", "mapping", "species"});
+    const Args a = parse_args(argc, argv, {"concatenate", "threads", "mapping", "species", "hash"});
+    const bool do_hash = a.boolean("hash", true);          // --hash 0: time the reader alone
     if (a.pos.size() < 2) die("usage: phylocsf_b200 dump-alignments [--concatenate BOOL] [--threads INT] <model> <alignments>...");
     Model model;
     load_model(model, a.pos[0], a.str("species"), a.str("mapping"));
@@ -559,7 +560,7 @@ int main_dump_alignments(int argc, char **argv) {
         for (const MafFile::Chain &c : maf.chains()) {
             maf.read_chain(c, aln, nullptr);
             uint64_t h = 1469598103934665603ull;
-            for (uint8_t b : aln.seqs) { h ^= b; h *= 1099511628211ull; }
+            if (do_hash) for (uint8_t b : aln.seqs) { h ^= b; h *= 1099511628211ull; }
             printf("%s\t%" PRId64 "\t%" PRId64 "\t%c\t%" PRId64 "\t%016" PRIx64 "\n", aln.chrom.c_str(), aln.start_pos, aln.chrom_len, aln.strand, aln.L, h);
         }
     }

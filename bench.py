@@ -247,7 +247,7 @@ def main():
             "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload, "sample_columns_per_step": S, "model": args.model},
+            "config": {"workload": workload, "sample_columns_per_step": S, "phylogenetic_model": args.model},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": ncores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}), file=json_out, flush=True)
@@ -398,7 +398,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": dtype, "data": "synthetic",
-            "config": {"workload": workload, "model": args.model, "leaves": nl, "columns_per_step_per_gpu": B,
+            "config": {"workload": workload, "phylogenetic_model": args.model, "leaves": nl, "columns_per_step_per_gpu": B,
                        "precision": args.precision,
                        "missing_fraction": 0.30, "l2_policy": "inputs larger than L2 (%.0f MB per step)" % (nl * B / 1e6),
                        "dedup": not args.no_dedup, "unique_pattern_ratio": tstats["n_unique"] / max(1, tstats["n_windows"]),

@@ -19,7 +19,7 @@ def test_reference_arm_prints_one_json_line():
     assert d["steps"] == 1 and d["warmup"] == 0 and d["value"] > 0 and d["ms_per_step"] > 0
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "columns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["metric"].startswith("MAF columns/sec") and d["config"]["model"] == "58mammals"
+    assert d["metric"].startswith("MAF columns/sec") and d["config"]["phylogenetic_model"] == "58mammals"
     # the kind is "reference" exactly when the shim-built reference binary is there
     assert (d["cpu_baseline"]["kind"] == "reference") == os.path.exists(os.path.join(ROOT, "oracle", "_ref", "phylocsf_ref"))
 

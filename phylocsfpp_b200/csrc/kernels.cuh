@@ -618,7 +618,7 @@ __global__ void k_scatter_list(uint32_t nwin, const uint32_t *__restrict__ pidx,
 constexpr int BLS_THREADS = 128;
 
 __global__ void __launch_bounds__(BLS_THREADS) k_bls(const uint8_t *__restrict__ codes, int64_t ld, int nl, int64_t L,
-                                                    const BlsNode *__restrict__ prog, int n_nodes, int depth,
+                                                    const BlsInner *__restrict__ prog, int n_inner, int depth,
                                                     double all, int raw, double *__restrict__ out) {
     extern __shared__ double bls_stack[];  // [depth][BLS_THREADS]
     const int64_t i = (int64_t)blockIdx.x * BLS_THREADS + threadIdx.x;
@@ -634,24 +634,26 @@ __global__ void __launch_bounds__(BLS_THREADS) k_bls(const uint8_t *__restrict__
     }
     double res = 0.0;
     if (cnt >= 2) {
+        // inner nodes in post-order; a leaf child contributes its own branch length (no stack traffic), an inner child the value on
+        // top of the stack (right child first: it was evaluated last).  Summation order = the reference's: (own + left) + right.
         double *st = bls_stack + threadIdx.x;
         int sp = 0;
-        for (int k = 0; k < n_nodes; ++k) {
-            const BlsNode e = prog[k];
-            if (e.is_leaf) { st[sp * BLS_THREADS] = e.bl; ++sp; continue; }
-            const double r = st[(sp - 1) * BLS_THREADS], l = st[(sp - 2) * BLS_THREADS];
-            sp -= 2;
-            const uint64_t rlo = e.self_lo & ~e.left_lo, rhi = e.self_hi & ~e.left_hi;
+        double v = 0.0;
+        for (int k = 0; k < n_inner; ++k) {
+            const BlsInner e = prog[k];
+            double r, l;
+            if (e.flags & 2) r = e.right_bl; else { --sp; r = st[sp * BLS_THREADS]; }
+            if (e.flags & 1) l = e.left_bl; else { --sp; l = st[sp * BLS_THREADS]; }
             const bool ol = ((mlo & e.left_lo) | (mhi & e.left_hi)) != 0;
-            const bool orr = ((mlo & rlo) | (mhi & rhi)) != 0;
+            const bool orr = ((mlo & e.self_lo & ~e.left_lo) | (mhi & e.self_hi & ~e.left_hi)) != 0;
             const bool arrived = ((mlo & ~e.self_lo) | (mhi & ~e.self_hi)) != 0;
-            double v = arrived ? e.bl : 0.0;
+            v = arrived ? e.bl : 0.0;
             if (ol) v = __dadd_rn(v, l);
             if (orr) v = __dadd_rn(v, r);
             st[sp * BLS_THREADS] = v;
             ++sp;
         }
-        res = st[0];
+        res = v;
         if (!raw) res = __ddiv_rn(res, all);
     }
     out[i] = res;

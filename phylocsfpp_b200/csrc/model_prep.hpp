@@ -37,6 +37,15 @@ struct BlsNode {            // one post-order entry of the BLS program
     int32_t pad;
 };
 
+struct BlsInner {           // one INNER node of the BLS program, post-order; leaf children are folded in (their value is their own
+    double bl;              // branch length, whatever the presence mask): half of the stack traffic of the node-per-entry program
+    double left_bl, right_bl;    // the child's branch length if it is a leaf
+    uint64_t self_lo, self_hi;
+    uint64_t left_lo, left_hi;
+    int32_t flags;          // bit 0: left child is a leaf, bit 1: right child is a leaf
+    int32_t pad;
+};
+
 struct EcmHost {
     double lambda[NS], SR[NS * NS], SRinv[NS * NS], pi[NS], logpi[NS];
     std::vector<double> P;        // (n-1) x 64 x 64 at rho = 1, row-major P[a][b]
@@ -67,6 +76,7 @@ struct ModelHost {
     int tc5_first[2] = {0, 0};         // the cherry the program starts with
     int tc5_smem_depth = 0;            // stack depth with the most pushes (kept in shared memory by k_prune_tc5)
     std::vector<BlsNode> bls_prog;
+    std::vector<BlsInner> bls_inner;
     int bls_depth = 0;
     double bls_all = 0.0;         // all_species_branch_length (additional_scores.hpp:56)
 };
@@ -329,6 +339,13 @@ inline void bls_walk(ModelHost &m, int i, uint64_t &lo, uint64_t &hi, int &depth
     lo = e.self_lo; hi = e.self_hi;
     depth_out = dl > dr + 1 ? dl : dr + 1;
     m.bls_prog.push_back(e);
+    BlsInner in{};
+    in.bl = e.bl;
+    const int cl = m.child1[i], cr = m.child2[i];
+    in.left_bl = m.bl64[cl]; in.right_bl = m.bl64[cr];
+    in.self_lo = e.self_lo; in.self_hi = e.self_hi; in.left_lo = llo; in.left_hi = lhi;
+    in.flags = (m.child1[cl] < 0 ? 1 : 0) | (m.child1[cr] < 0 ? 2 : 0);
+    m.bls_inner.push_back(in);
 }
 }  // namespace detail
 
@@ -421,6 +438,7 @@ inline std::string prepare_model(ModelHost &m, int nl, const int16_t *c1, const 
     // BLS program
     uint64_t lo, hi;
     m.bls_prog.clear();
+    m.bls_inner.clear();
     detail::bls_walk(m, m.n - 1, lo, hi, m.bls_depth);
     {
         const uint64_t alo = nl >= 64 ? ~0ull : ((1ull << nl) - 1);

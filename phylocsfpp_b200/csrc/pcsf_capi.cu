@@ -85,7 +85,7 @@ struct pcsf_model {
     int tc5h_nstage = 2, tc5h_nlstage = 3;
     bool tc5_half = false;
     int32_t *d_program = nullptr;
-    BlsNode *d_bls_prog = nullptr;
+    BlsInner *d_bls_prog = nullptr;
     float *d_bl = nullptr;
     int32_t *d_gemm_edges = nullptr;
     // scratch
@@ -175,7 +175,7 @@ extern "C" pcsf_status pcsf_model_create(const pcsf_model_desc *d, int device, p
     m->prune_tc5h_smem = prune_tc5h_smem_bytes(m->host.nl, (int)m->host.tc5_steps.size(), m->tc5h_nstage, m->tc5h_nlstage);
     CK(cudaFuncSetAttribute(k_prune_tc5h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->prune_tc5h_smem));
     if (const char *e = getenv("PCSF_TC5_VARIANT")) m->tc5_half = strcmp(e, "half") == 0;
-    if ((st = upload(m->host.bls_prog.data(), m->host.bls_prog.size() * sizeof(BlsNode), (void **)&m->d_bls_prog))) return st;
+    if ((st = upload(m->host.bls_inner.data(), m->host.bls_inner.size() * sizeof(BlsInner), (void **)&m->d_bls_prog))) return st;
     if ((st = upload(m->host.bl.data(), m->host.bl.size() * 4, (void **)&m->d_bl))) return st;
     {
         std::vector<int32_t> ge(m->host.gemm_edges.begin(), m->host.gemm_edges.end());
@@ -437,7 +437,7 @@ static pcsf_status run_bls(pcsf_model *m, int64_t L, int raw, double *d_out, cud
     if (L <= 0) return PCSF_OK;
     const size_t sh = (size_t)std::max(1, m->host.bls_depth) * BLS_THREADS * 8;
     m->launches++; k_bls<<<(unsigned)((L + BLS_THREADS - 1) / BLS_THREADS), BLS_THREADS, sh, st>>>(
-        m->codes.as<uint8_t>(), m->codes_ld, m->host.nl, L, m->d_bls_prog, (int)m->host.bls_prog.size(),
+        m->codes.as<uint8_t>(), m->codes_ld, m->host.nl, L, m->d_bls_prog, (int)m->host.bls_inner.size(),
         m->host.bls_depth, m->host.bls_all, raw, d_out);
     CK(cudaGetLastError());
     return PCSF_OK;
@@ -456,7 +456,7 @@ static pcsf_status run_bls_segment(pcsf_model *m, int64_t s0, int64_t s1, double
     if (s1 <= s0) return PCSF_OK;
     const size_t sh = (size_t)std::max(1, m->host.bls_depth) * BLS_THREADS * 8;
     m->launches++; k_bls<<<(unsigned)((s1 - s0 + BLS_THREADS - 1) / BLS_THREADS), BLS_THREADS, sh, st>>>(
-        m->codes.as<uint8_t>() + s0, m->codes_ld, m->host.nl, s1 - s0, m->d_bls_prog, (int)m->host.bls_prog.size(),
+        m->codes.as<uint8_t>() + s0, m->codes_ld, m->host.nl, s1 - s0, m->d_bls_prog, (int)m->host.bls_inner.size(),
         m->host.bls_depth, m->host.bls_all, 0, d_out + s0);
     CK(cudaGetLastError());
     return PCSF_OK;

@@ -222,3 +222,175 @@ def test_build_tracks_cli_multiple_files(golden_dir, tmp_path):
         ab = open(os.path.join(outs["ab"], n), "rb").read()
         assert ab == a + b, n
         assert a == gzip.open(os.path.join(R, "tracks12." + n + ".gz"), "rb").read(), n
+
+
+def _py_hmm_smooth(params, runs):
+    """Independent restatement of the smoothing stage in plain Python (reference src/create_tracks.hpp:86-158, 162-200, 226-235):
+    params = (coding_prior, coding_codons, [w0, w1, w2], [n0, n1, n2]); runs = [(chrom, start, [scores])] -> wig text."""
+    import math
+    from phylocsfpp_b200.tracks import my_format
+    prior, ccod, w, n = params
+    unnorm = [w[i] * n[i] for i in range(3)]
+    c2nc = [w[i] / ccod for i in range(3)]
+    nc2c = [1.0 / n[i] for i in range(3)]
+    init = [prior] + [(1 - prior) * unnorm[i] / (unnorm[0] + unnorm[1] + unnorm[2]) for i in range(3)]
+    T = [[0.0] * 4 for _ in range(4)]
+    T[0][0] = 1.0 - (c2nc[0] + c2nc[1] + c2nc[2])
+    for j in range(3):
+        T[0][j + 1] = c2nc[j]
+    for i in range(1, 4):
+        T[i][0] = nc2c[i - 1]
+        T[i][i] = 1.0 - nc2c[i - 1]
+    emit = lambda s, x: math.pow(10, x / 10) if s == 0 else 1
+    out = []
+    for chrom, start, obs in runs:
+        N = len(obs)
+        f = [[init[s] * emit(s, obs[0]) for s in range(4)]]
+        for p in range(1, N):
+            row = []
+            for s in range(4):
+                acc = 0.0
+                for q in range(4):
+                    acc += f[p - 1][q] * T[q][s]
+                row.append(acc * emit(s, obs[p]))
+            mx = max(0.0, *row)
+            f.append([v / mx for v in row])
+        b = [[1.0] * 4 for _ in range(N)]
+        for p in range(N - 2, -1, -1):
+            row = []
+            for s in range(4):
+                acc = 0.0
+                for q in range(4):
+                    acc += (T[s][q] * emit(q, obs[p + 1]) * b[p + 1][q])
+                row.append(acc)
+            mx = max(0.0, *row)
+            b[p] = [v / mx for v in row]
+        out.append(f"fixedStep chrom={chrom} start={start} step=3 span=3")
+        for p in range(N):
+            tot = 0.0
+            for s in range(4):
+                tot += f[p][s] * b[p][s]
+            pr = (f[p][0] * b[p][0]) / tot
+            if pr < math.pow(10, -15.0):
+                lo = -15.0
+            elif pr > 1 - math.pow(10, -15.0):
+                lo = 15.0
+            else:
+                lo = math.log10(pr / (1 - pr))
+            out.append(my_format("%.3f", np.float32(lo)))
+    return out
+
+
+def test_hmm_smoothing_against_plain_python(golden_dir, tmp_path):
+    """hmm.hpp's forward-backward against an independent plain-Python restatement on hand-made raw tracks: two runs that continue
+    each other (joined, wig_file_reader.hpp:111-127), a gap, another chromosome, a single-codon run, extreme scores (log-odds clipped
+    at +-15).  HMM parameters as estimated by the tool itself from the smooth53 exon list (--print-hmm)."""
+    _need_bin()
+    _, exons, glen = _smooth_inputs(golden_dir, tmp_path, "smooth53")
+    raw = os.path.join(str(tmp_path), "handmade")
+    os.makedirs(raw)
+    rng = np.random.default_rng(3)
+    sc = lambda n, mu: [float(np.float32(x)) for x in np.round(rng.normal(mu, 8.0, n), 3)]
+    pieces = [("chr1", 100, sc(40, -5)), ("chr1", 100 + 3 * 40, sc(25, 12)),          # continues -> one run of 65
+              ("chr1", 1000, sc(1, 3)), ("chr2", 7, [300.0, -300.0, 250.0] + sc(30, 0)), ("chr2", 400, sc(12, 40))]
+    from phylocsfpp_b200.tracks import my_format
+    for k in FRAMES6:
+        with open(os.path.join(raw, f"PhyloCSFRaw{k}.wig"), "w") as fh:
+            for chrom, start, vals in pieces:
+                fh.write(f"fixedStep chrom={chrom} start={start} step=3 span=3\n")
+                for v in vals:
+                    fh.write(my_format("%.3f", np.float32(v)) + "\n")
+    out = os.path.join(str(tmp_path), "handmade_out")
+    r = subprocess.run([BIN, "smooth-tracks", "--genome-length", glen, "--coding-exons", exons, "--output-regions", "0", "--print-hmm", "1", raw, out],
+                       check=True, capture_output=True, text=True)
+    vals = {ln.split()[0] if not ln.startswith("nc") else "nc" + ln.split()[1]: ln.split() for ln in r.stdout.splitlines() if ln.strip()}
+    params = (float(vals["coding_prior"][1]), float(vals["coding_codons"][1]), [float(vals[f"nc{i}"][3]) for i in range(3)],
+              [float(vals[f"nc{i}"][5]) for i in range(3)])
+    runs = [("chr1", 100, [float(my_format("%.3f", np.float32(v))) for v in pieces[0][2] + pieces[1][2]]),
+            ("chr1", 1000, [float(my_format("%.3f", np.float32(v))) for v in pieces[2][2]]),
+            ("chr2", 7, [float(my_format("%.3f", np.float32(v))) for v in pieces[3][2]]),
+            ("chr2", 400, [float(my_format("%.3f", np.float32(v))) for v in pieces[4][2]])]
+    expect = _py_hmm_smooth(params, runs)
+    got = open(os.path.join(out, "PhyloCSF+1.wig")).read().split("\n")
+    assert got[-1] == "" and got[:-1] == expect
+    assert "15.0" in expect or "-15.0" in expect          # the clipping branch was exercised
+
+
+def test_fixed_mean_against_reference_on_cpu(golden_dir, tmp_path):
+    """score-msa --strategy fixed_mean restated on the CPU: per-codon decibans from the oracle (run_tracks), the plain-Python HMM above
+    with the parameters the host estimates from the synthetic exon list (> 20 000 gaps: the std::shuffle path), mean log-odds summed in a
+    float (score_msa.hpp:152-213) — against the reference's own output for msa29."""
+    _need_bin()
+    import math
+    from oracle import oracle as orc
+    from tests.util import write_synthetic_exons
+    SPECIES29 = "Human,Chimp,Mouse,Dog,Cow,Horse,Elephant,Armadillo,Rat,Rabbit,Cat,Megabat"
+    R = os.path.join(golden_dir, "ref-generated")
+    exons = os.path.join(str(tmp_path), "exons.txt")
+    write_synthetic_exons(exons)
+    raw = os.path.join(str(tmp_path), "empty_raw")
+    os.makedirs(raw)
+    for k in FRAMES6:
+        open(os.path.join(raw, f"PhyloCSFRaw{k}.wig"), "w").close()
+    r = subprocess.run([BIN, "smooth-tracks", "--genome-length", "400000000", "--coding-exons", exons, "--print-hmm", "1", raw,
+                        os.path.join(str(tmp_path), "o")], check=True, capture_output=True, text=True)
+    vals = {ln.split()[0] if not ln.startswith("nc") else "nc" + ln.split()[1]: ln.split() for ln in r.stdout.splitlines() if ln.strip()}
+    params = (float(vals["coding_prior"][1]), float(vals["coding_codons"][1]), [float(vals[f"nc{i}"][3]) for i in range(3)],
+              [float(vals[f"nc{i}"][5]) for i in range(3)])
+    m = load_model("29mammals", SPECIES29)
+    mc, mnc = orc.OracleModel(m.tree, m.S_c, m.f_c), orc.OracleModel(m.tree, m.S_nc, m.f_nc)
+    alns = list(MafReader(os.path.join(R, "msa29.maf.gz"), m.seqid_to_phyloid, m.nl, False, warn=False))
+    gold = [ln.rstrip("\n").split("\t") for ln in open(os.path.join(R, "msa29.fixed_mean.scores")) if not ln.startswith("#") and not ln.startswith("seq\t")]
+    assert len(alns) == len(gold)
+    for a, g in list(zip(alns, gold))[::3]:
+        scores = [float(x) for x in orc.run_tracks(mc, mnc, orc.translate(a.seqs))]
+        if not scores:
+            continue
+        lines = _py_hmm_smooth_values(params, scores)
+        acc = np.float32(0.0)
+        for v in lines:
+            acc = np.float32(float(acc) + v)
+        mean = np.float32(acc) / np.float32(len(lines))
+        assert abs(float(mean) - float(g[4])) <= 2e-5, (a.start_pos, float(mean), g[4])
+
+
+def _py_hmm_smooth_values(params, obs):
+    """Posterior log-odds (doubles, unformatted) of one run: the numeric core of _py_hmm_smooth."""
+    import math
+    prior, ccod, w, n = params
+    unnorm = [w[i] * n[i] for i in range(3)]
+    c2nc = [w[i] / ccod for i in range(3)]
+    nc2c = [1.0 / n[i] for i in range(3)]
+    init = [prior] + [(1 - prior) * unnorm[i] / (unnorm[0] + unnorm[1] + unnorm[2]) for i in range(3)]
+    T = [[0.0] * 4 for _ in range(4)]
+    T[0][0] = 1.0 - (c2nc[0] + c2nc[1] + c2nc[2])
+    for j in range(3):
+        T[0][j + 1] = c2nc[j]
+    for i in range(1, 4):
+        T[i][0] = nc2c[i - 1]
+        T[i][i] = 1.0 - nc2c[i - 1]
+    emit = lambda s, x: math.pow(10, x / 10) if s == 0 else 1
+    N = len(obs)
+    f = [[init[s] * emit(s, obs[0]) for s in range(4)]]
+    for p in range(1, N):
+        row = [sum_in_order([f[p - 1][q] * T[q][s] for q in range(4)]) * emit(s, obs[p]) for s in range(4)]
+        mx = max(0.0, *row)
+        f.append([v / mx for v in row])
+    b = [[1.0] * 4 for _ in range(N)]
+    for p in range(N - 2, -1, -1):
+        row = [sum_in_order([(T[s][q] * emit(q, obs[p + 1]) * b[p + 1][q]) for q in range(4)]) for s in range(4)]
+        mx = max(0.0, *row)
+        b[p] = [v / mx for v in row]
+    out = []
+    for p in range(N):
+        tot = sum_in_order([f[p][s] * b[p][s] for s in range(4)])
+        pr = (f[p][0] * b[p][0]) / tot
+        out.append(-15.0 if pr < math.pow(10, -15.0) else 15.0 if pr > 1 - math.pow(10, -15.0) else math.log10(pr / (1 - pr)))
+    return out
+
+
+def sum_in_order(xs):
+    acc = 0.0
+    for x in xs:
+        acc += x
+    return acc

@@ -359,3 +359,29 @@ def test_differential_cli_vs_reference_binary(tmp_path, model_name, cols, seed, 
     subprocess.run([BIN, "build-tracks", "--threads", "3", "--output", our_out] + extra + [model_name, maf], check=True, capture_output=True)
     for n in WIGS:
         assert open(os.path.join(our_out, n), "rb").read() == open(os.path.join(ref_out, n), "rb").read(), n
+
+
+def test_differential_omega_oracle_vs_reference_binary(tmp_path):
+    """OMEGA on fresh single-block alignments (7yeast): the reference binary against orc_omega, at the reference's CI tolerance for this
+    strategy (squared error <= 0.1, test/tests.sh:46); most rows agree far better."""
+    _need_ref()
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    os.environ["PCSF_SYNTH_CPU"] = "1"
+    from make_synth_maf import write_synth_maf
+    m = load_model("7yeast")
+    maf = os.path.join(str(tmp_path), "b.maf")
+    write_synth_maf(maf, m, 1500, seed=51, loguniform_blocks=(30, 300), alien_p=0.0)
+    alns = list(MafReader(maf, m.seqid_to_phyloid, m.nl, False, warn=False))
+    out = os.path.join(str(tmp_path), "o")
+    subprocess.run([REF, "score-msa", "--threads", "8", "--strategy", "omega", "--comp-phylo", "1", "--comp-anc", "0", "--output", out, "7yeast", maf],
+                   check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    gold = _rows(os.path.join(out, "b.maf.scores"))
+    assert len(gold) == len(alns) >= 6
+    d = []
+    for a, g in zip(alns, gold):
+        s, info = orc.run_omega(m.tree, orc.translate(a.seqs))
+        assert info["status"] == 0
+        d.append(abs(float(s) - float(g[4])))
+    assert max(d) ** 2 <= 0.1, d
+    assert sorted(d)[len(d) // 2] <= 0.02, d

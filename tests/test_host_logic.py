@@ -134,3 +134,23 @@ def test_bls_restatement_small():
     # column 1: human+chimp only -> their two leaf branches
     assert abs(per[1] - (t.branch_len_f64[0] + t.branch_len_f64[1]) / total) < 1e-15
     assert abs(score - per.sum() / 4) < 1e-15
+
+
+def test_synthetic_workload_has_the_baseline_shape():
+    """The bench / fixture generator: deterministic per seed, reference row complete, ~30 % of the other cells
+    missing ('-' or 'N'), only characters the reference accepts, both coding-like and non-coding-like stretches."""
+    import torch
+    from phylocsfpp_b200.models import load_model
+    from phylocsfpp_b200.synth import synth_alignment
+    m = load_model("58mammals")
+    L = 60000
+    a = synth_alignment(m, L, seed=5, device="cpu")[:, :L].numpy()
+    b = synth_alignment(m, L, seed=5, device="cpu")[:, :L].numpy()
+    assert a.shape == (m.nl, L) and (a == b).all()
+    assert set(np.unique(a).tolist()) <= set(b"ACGTacgtN-")
+    ref_missing = np.isin(a[0], np.frombuffer(b"N-", np.uint8)).mean()
+    other_missing = np.isin(a[1:], np.frombuffer(b"N-", np.uint8)).mean()
+    assert ref_missing == 0.0
+    assert 0.25 <= other_missing <= 0.36, other_missing
+    c = synth_alignment(m, L, seed=6, device="cpu")[:, :L].numpy()
+    assert (a != c).mean() > 0.3

@@ -118,10 +118,27 @@ void warn_unresolved(const MafFile &maf) {
         printf("\033[33mWARNING: Not able to match species %s in alignment file to model (Use `--mapping` to fix it)!\033[0m\n", s.c_str());
 }
 
+// --model-info NAME (run.hpp:213-232): the species of a model with their alternative names; no GPU involved.
+int print_model_info(const std::string &model_name) {
+    Model model;
+    load_model(model, model_name, "", "");
+    printf("The model %s contains the following species.\n\n", model_name.c_str());
+    printf("%35s\t%s\n", "Species name", "Alternative name(s)");
+    for (const std::string &label : model.tree.labels) {
+        if (label.empty()) continue;
+        std::string alt;
+        auto it = model.aliases.find(label);
+        if (it != model.aliases.end()) for (const std::string &sn : it->second) alt += sn + " ";
+        printf("%35s\t%s\n", label.c_str(), alt.c_str());
+    }
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------- build-tracks
 int main_build_tracks(int argc, char **argv) {
     const Args a = parse_args(argc, argv, {"output-raw-phylo", "output-phylo", "output-regions", "power-threshold", "genome-length", "coding-exons",
-                                           "threads", "output", "mapping", "species", "gpus", "precision"});
+                                           "threads", "output", "mapping", "species", "gpus", "precision", "model-info"});
+    if (a.has("model-info")) return print_model_info(a.str("model-info"));          // build_tracks.hpp:401-405
     if (a.pos.size() < 2) die("usage: phylocsf_b200 build-tracks [OPTIONS] <model> <alignments>...");
     const bool keep_raw = a.boolean("output-raw-phylo", true);
     const bool smooth = a.boolean("output-phylo", false), regions = a.boolean("output-regions", false);
@@ -386,7 +403,8 @@ int main_build_tracks(int argc, char **argv) {
 // ---------------------------------------------------------------------------------------------- score-msa
 int main_score_msa(int argc, char **argv) {
     const Args a = parse_args(argc, argv, {"strategy", "comp-phylo", "comp-anc", "comp-bls", "threads", "output", "mapping", "species", "gpus",
-                                           "genome-length", "coding-exons"});
+                                           "genome-length", "coding-exons", "model-info"});
+    if (a.has("model-info")) return print_model_info(a.str("model-info"));          // score_msa.hpp:291-295
     if (a.pos.size() < 2) die("usage: phylocsf_b200 score-msa [OPTIONS] <model> <alignments>...");
     const std::string strat = lower(a.str("strategy", "mle"));
     pcsf_strategy strategy;

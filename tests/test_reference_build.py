@@ -385,3 +385,13 @@ def test_differential_omega_oracle_vs_reference_binary(tmp_path):
         d.append(abs(float(s) - float(g[4])))
     assert max(d) ** 2 <= 0.1, d
     assert sorted(d)[len(d) // 2] <= 0.02, d
+
+
+@pytest.mark.parametrize("model_name", ["100vertebrates", "53birds", "23flies", "7yeast"])
+def test_model_info_matches_reference_binary(model_name):
+    """--model-info (run.hpp:213-232): species and alternative names, identical text from both tools and both sub-commands."""
+    _need_ref()
+    for tool in ("build-tracks", "score-msa"):
+        ours = subprocess.run([BIN, tool, "--model-info", model_name], capture_output=True, text=True, check=True).stdout
+        ref = subprocess.run([REF, tool, "--model-info", model_name], capture_output=True, text=True, check=True).stdout
+        assert ours == ref and model_name in ours and len(ours.splitlines()) > 5

@@ -185,9 +185,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-port", action="store_true", help="time the oracle port instead of the reference binary on the CPU legs")
     ap.add_argument("--no-dedup", action="store_true")
-    ap.add_argument("--precision", default="tc5", choices=["f64", "f32", "tc5"],
+    ap.add_argument("--precision", default="tc5", choices=["f64", "tc5"],
                     help="tc5: tcgen05/TMEM split-TF32 path (fastest path inside the 1e-3 deciban contract); "
-                         "f64: FP64 DMMA path (parity anchor, byte-identical wig text); f32: split-TF32 mma.sync path")
+                         "f64: FP64 DMMA path (parity anchor, byte-identical wig text)")
     args = ap.parse_args()
 
     # stdout carries exactly one JSON line: libraries that write to fd 1 (NCCL prints its version banner there at
@@ -274,7 +274,7 @@ def main():
     minus = torch.empty(Wn, dtype=torch.float64, device=dev)
     bls = torch.empty(B, dtype=torch.float64, device=dev)
     flags = (capi.TRACKS_SCORES | capi.TRACKS_BLS | (capi.TRACKS_NO_DEDUP if args.no_dedup else 0)
-             | {"f64": 0, "f32": capi.TRACKS_FP32, "tc5": capi.TRACKS_TC5}[args.precision])
+             | {"f64": 0, "tc5": capi.TRACKS_TC5}[args.precision])
     stream = torch.cuda.current_stream()
 
     def step():
@@ -343,9 +343,9 @@ def main():
     # one instrumented step of the other precisions, for the side-by-side the north star asks for
     other = {}
     if rank == 0:
-        base = flags & ~(capi.TRACKS_FP32 | capi.TRACKS_TC5)
+        base = flags & ~capi.TRACKS_TC5
         dm.set_timing(True)
-        for pname, pflag in (("f64", 0), ("f32", capi.TRACKS_FP32), ("tc5", capi.TRACKS_TC5)):
+        for pname, pflag in (("f64", 0), ("tc5", capi.TRACKS_TC5)):
             if pname == args.precision:
                 continue
             dm.tracks_device(seqs.data_ptr(), B, ld, base | pflag, plus.data_ptr(), minus.data_ptr(), bls.data_ptr(), 0, stream.cuda_stream)
@@ -387,7 +387,7 @@ def main():
         else:
             # executed tensor flops per pruning: every inner edge is a (window x 64 x 64) product done as 3 TF32 products
             # (hi*hi, hi*lo, lo*hi) on either tensor path; leaf edges are gathers (no tensor work) on both
-            kernel, dtype = ("k_prune_f32", "tf32x3/f32") if args.precision == "f32" else ("k_prune_tc5", "tf32x3/f32")
+            kernel, dtype = "k_prune_tc5", "tf32x3/f32"
             peak = peaks.get("tf32_tflops", 764.2)
             peak_source = ("dense TF32 tensor peak = cuBLAS TF32 GEMM 8192^3 measured on this pool (profiles/peaks_fp64.json; "
                            "MEASURED_PEAKS.json carries bf16 only: 1605 TFLOP/s burst, TF32 is half rate); `achieved` counts "

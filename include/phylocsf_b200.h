@@ -85,8 +85,8 @@ int pcsf_abi_version(void);
 #define PCSF_TRACKS_SCORES   0x1u  /* plus[]/minus[] decibans */
 #define PCSF_TRACKS_BLS      0x2u  /* bls[] */
 #define PCSF_TRACKS_NO_DEDUP 0x4u  /* prune every window, do not deduplicate site patterns */
-#define PCSF_TRACKS_FP32     0x8u  /* FP32-class tensor path: split-TF32 mma.sync + per-window log-scaling (|delta| <= 1e-3 decibans) */
-#define PCSF_TRACKS_TC5      0x10u /* FP32-class path on tcgen05/TMEM (5th-gen tensor cores), same contract as FP32 */
+/* 0x8u was PCSF_TRACKS_FP32 (split-TF32 on mma.sync, round 1): superseded by the tcgen05 path and removed from the library */
+#define PCSF_TRACKS_TC5      0x10u /* FP32-class arithmetic on tcgen05/TMEM (5th-gen tensor cores): split TF32 + per-window log-scaling, |delta| <= 1e-3 decibans */
 
 typedef struct {
     int64_t n_windows;        /* 2 * max(L-2, 0) */

@@ -24,7 +24,6 @@ PCSF_ERR_BAD_CHAR = 37
 TRACKS_SCORES = 0x1
 TRACKS_BLS = 0x2
 TRACKS_NO_DEDUP = 0x4
-TRACKS_FP32 = 0x8
 TRACKS_TC5 = 0x10
 
 STRATEGY_MLE = 0
@@ -144,7 +143,7 @@ class DeviceModel:
         return lam, pi, P
 
     def tracks(self, seqs: np.ndarray, scores: bool = True, bls: bool = True, dedup: bool = True,
-               want_patterns: bool = False, fp32: bool = False, tc5: bool = False):
+               want_patterns: bool = False, tc5: bool = False):
         """Host-buffer call (H2D + kernels + D2H).  seqs: uint8 ASCII [nl, L].
         Returns dict(plus, minus, bls, pattern_index, stats)."""
         seqs = np.ascontiguousarray(seqs, np.uint8)
@@ -152,7 +151,7 @@ class DeviceModel:
         assert nl == self.nl
         W = max(Lc - 2, 0)
         flags = ((TRACKS_SCORES if scores else 0) | (TRACKS_BLS if bls else 0) | (0 if dedup else TRACKS_NO_DEDUP)
-                 | (TRACKS_FP32 if fp32 else 0) | (TRACKS_TC5 if tc5 else 0))
+                 | (TRACKS_TC5 if tc5 else 0))
         plus = np.zeros(W, np.float64) if scores else None
         minus = np.zeros(W, np.float64) if scores else None
         b = np.zeros(Lc, np.float64) if bls else None

@@ -176,10 +176,26 @@ __global__ void k_keys_list(WinSpace ws, int64_t nwin, uint64_t *__restrict__ kl
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Dedup: open-addressing table of window ids keyed by the 128-bit pattern key.
+// Dedup: open-addressing table of window ids keyed by the 128-bit pattern key; a key match is confirmed on the codon columns.
 constexpr uint32_t EMPTY = 0xFFFFFFFFu;
 
-__global__ void k_insert(const uint64_t *__restrict__ klo, const uint64_t *__restrict__ khi, uint32_t nwin,
+// The nl codon ids of two windows, compared one by one.  Only windows whose 128-bit keys are equal get here (i.e. duplicates pay
+// for it, nl x 6 byte loads), and it makes pattern identity exact instead of "equal up to a 128-bit hash collision".
+__device__ __forceinline__ bool same_pattern(const WinSpace &ws, uint32_t w1, uint32_t w2) {
+    int64_t o1, o2;
+    uint32_t s1 = 0, s2 = 0;
+    if (ws.mode == 0) { o1 = ws.c0 + (w1 >> 1); s1 = w1 & 1; o2 = ws.c0 + (w2 >> 1); s2 = w2 & 1; }
+    else { o1 = ws.win_off[w1]; o2 = ws.win_off[w2]; }
+    const uint8_t *p = ws.codes + o1, *q = ws.codes + o2;
+    for (int s = 0; s < ws.nl; ++s, p += ws.ld, q += ws.ld) {
+        const uint32_t a = s1 ? codon_minus(p[0], p[1], p[2]) : codon_plus(p[0], p[1], p[2]);
+        const uint32_t b = s2 ? codon_minus(q[0], q[1], q[2]) : codon_plus(q[0], q[1], q[2]);
+        if (a != b) return false;
+    }
+    return true;
+}
+
+__global__ void k_insert(WinSpace ws, const uint64_t *__restrict__ klo, const uint64_t *__restrict__ khi, uint32_t nwin,
                          uint32_t *table, uint32_t tmask, uint32_t *__restrict__ slot_of, uint32_t *slotmin) {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= nwin) return;
@@ -192,7 +208,7 @@ __global__ void k_insert(const uint64_t *__restrict__ klo, const uint64_t *__res
             if (prev == EMPTY) break;
             cur = prev;
         }
-        if (cur == w || (klo[cur] == a && khi[cur] == b)) break;
+        if (cur == w || (klo[cur] == a && khi[cur] == b && same_pattern(ws, w, cur))) break;
         slot = (slot + 1) & tmask;
     }
     slot_of[w] = slot;

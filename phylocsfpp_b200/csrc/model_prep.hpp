@@ -51,13 +51,13 @@ struct EcmHost {
     std::vector<double> P;        // (n-1) x 64 x 64 at rho = 1, row-major P[a][b]
     std::vector<double> pstream;  // n_gemm tiles of 4096 doubles, DMMA fragment order, program order
     std::vector<double> leafPT;   // nl x 65 x 64: leafPT[l][x][a] = P_l[a][x], x = 64 -> row sums
-    // FP32-class tensor path (split TF32): tiles of 2048 float4 {hi0, hi1, lo0, lo1}, HMMA.1688 fragment order
-    std::vector<float> pstream32;
-    std::vector<float> leafPT32;  // nl x 65 x 64 floats
-    // tcgen05 path: one 32 KB tile per inner edge in step order (UMMA K-major no-swizzle B layout, N = 128 = [hi | lo])
-    // and one 17 KB shared-memory gather table per leaf in program order (64 rows x 68 floats)
+    // tcgen05 path: one 32 KB tile per inner NON-CHERRY edge in step order (UMMA K-major no-swizzle B layout, N = 128 =
+    // [hi | lo]), one 17 KB shared-memory gather table per DIRECT leaf (a leaf whose sibling is not a leaf) in program order
+    // (64 rows x 68 floats), and, per cherry in program order, what k_build_cherry needs to tabulate the message of the edge
+    // above it: the cherry node's own P (row-major FP64) — the two leaves' columns come from leafPT
     std::vector<float> pstream_tc5;
     std::vector<float> leaf_tc5;
+    std::vector<double> cherry_P;   // n_cherry x 64 x 64
 };
 
 struct ModelHost {
@@ -69,12 +69,14 @@ struct ModelHost {
     std::vector<int32_t> program;
     std::vector<int> gemm_edges;  // node id of the g-th GEMM op
     int max_stack = 0;
-    // tcgen05 path: the same program as one step per inner edge (GEMM) + what follows it up to the next GEMM
-    std::vector<uint32_t> tc5_steps;   // leaf1 | leaf2 << 8 | post-op << 16 | END << 20
+    // tcgen05 path (prepare_tc5_program): one step per GEMM (non-cherry inner edge) + what follows it up to the next GEMM
+    std::vector<uint32_t> tc5_steps;   // src1 | src2 << 8 | post-op << 16 | END << 20
     std::vector<int> tc5_edges;        // node id of the edge of step s
-    std::vector<int> tc5_leaf_order;   // leaves in the order the program gathers them
-    int tc5_first[2] = {0, 0};         // the cherry the program starts with
-    int tc5_smem_depth = 0;            // stack depth with the most pushes (kept in shared memory by k_prune_tc5)
+    std::vector<int> tc5_leaf_order;   // direct leaves in the order the program gathers them (the leaf-table ring)
+    std::vector<int> tc5_cherries;     // cherry node ids in the order the program consumes their tables
+    std::vector<uint16_t> tc5_cherry_leaves;   // left leaf | right leaf << 8 of cherry k
+    uint32_t tc5_start = 0;            // src1 | src2 << 8 of the chain start the program begins with
+    int tc5_max_stack = 0;             // pushes alive at once (depth of the global-memory stack)
     std::vector<BlsNode> bls_prog;
     std::vector<BlsInner> bls_inner;
     int bls_depth = 0;
@@ -221,28 +223,18 @@ inline float tf32_rna(float x) {
     return r;
 }
 
-// mma.sync.m16n8k8.tf32 B-fragment order of one 64x64 P for the chained, K-permuted GEMM of k_prune_f32:
-//   tile[ks][nt][lane] = float4{hi(P[a][b0]), hi(P[a][b1]), lo(P[a][b0]), lo(P[a][b1])},
-//   a = 8*nt + lane/4, b0 = 8*ks + 2*(lane%4), b1 = b0 + 1; p ~= hi + lo with hi, lo in TF32.
-inline void to_fragment_order_tf32(const double *P, float *tile) {
-    for (int ks = 0; ks < 8; ++ks)
-        for (int nt = 0; nt < 8; ++nt)
-            for (int lane = 0; lane < 32; ++lane) {
-                const int a = 8 * nt + lane / 4, b0 = 8 * ks + 2 * (lane % 4);
-                float *o = tile + ((size_t)(ks * 8 + nt) * 32 + lane) * 4;
-                for (int e = 0; e < 2; ++e) {
-                    const double p = P[a * NS + b0 + e];
-                    const float hi = tf32_rna((float)p);
-                    const float lo = tf32_rna((float)(p - (double)hi));
-                    o[e] = hi;
-                    o[2 + e] = lo;
-                }
-            }
-}
-
 // ---- tcgen05 path ------------------------------------------------------------------------------------------
-// Step word: bits 0-7 leaf1, 8-15 leaf2, 16-17 post-op (what the program does between this GEMM and the next), bit 20 END.
-enum : uint32_t { T5_NONE = 0, T5_MUL_LEAF = 1, T5_PUSH_CHERRY = 2, T5_POP_MUL = 3, T5_END = 1u << 20 };
+// Sources of a factor that is not a GEMM result.  A LEAF's message is column x of P_l (gathered from a shared-memory table);
+// a CHERRY's message (the edge above a node whose two children are leaves) depends only on the two leaves' codons, so it is
+// tabulated once per model: T_c[x][y][a] = sum_b P_c[a][b] P_l[b][x] P_r[b][y], x, y in 0..64 (64 = gap/N: all ones),
+// 4225 rows of 64 floats in global memory (L2), and GATHERED — no GEMM, no leaf gathers, no stack push for that edge.
+//   source byte: bit 7 = cherry, bits 0-6 = leaf id (leaf) / cherry number in program order (cherry)
+// Step word: bits 0-7 src1, 8-15 src2, 16-17 post-op (what the program does between this GEMM and the next), bit 20 END.
+//   T5_MUL         alpha_parent = msg * src1
+//   T5_PUSH_START  push msg; alpha of a new chain = src1 * src2 (a node whose two children are leaves / cherries)
+//   T5_POP_MUL     alpha_parent = msg * pop
+enum : uint32_t { T5_NONE = 0, T5_MUL = 1, T5_PUSH_START = 2, T5_POP_MUL = 3, T5_END = 1u << 20, T5_SRC_CHERRY = 0x80u };
+constexpr int T5_CHERRY_ROWS = 65 * 65;
 constexpr int T5_LEAF_ROW = 68;                      // floats per gather-table row: 272 B stride spreads the rows over the banks
 constexpr int T5_LEAF_FLOATS = 64 * T5_LEAF_ROW;     // 17408 B per leaf
 
@@ -319,6 +311,91 @@ inline void emit_partial(ModelHost &m, int i, const std::vector<int> &need, int 
         --sp;
     }
 }
+// ---- tcgen05 path program (cherry tables) -------------------------------------------------------------------------
+// Node kinds: 'L' leaf, 'C' cherry (both children leaves; not the root: its message is tabulated), 'I' every other
+// inner node.  Only edges above 'I' nodes are GEMMs.
+struct Tc5Emit {
+    ModelHost &m;
+    std::vector<char> kind;
+    std::vector<int> need;                // live partials needed to evaluate the subtree (Strahler number over 'I' nodes)
+    std::vector<uint32_t> ops;            // (code << 16) | a | b << 8: 1 START(a, b), 2 GEMM, 3 MUL(a), 4 PUSH, 5 POP_MUL
+    std::vector<int> op_edge;             // node id for GEMM ops
+    int sp = 0;
+    explicit Tc5Emit(ModelHost &mm) : m(mm), kind(mm.n), need(mm.n, 0) {}
+    void classify(int i) {
+        if (m.child1[i] < 0) { kind[i] = 'L'; return; }
+        classify(m.child1[i]); classify(m.child2[i]);
+        const bool cherry = kind[m.child1[i]] == 'L' && kind[m.child2[i]] == 'L' && i != m.n - 1;
+        kind[i] = cherry ? 'C' : 'I';
+        if (kind[i] == 'I') {
+            const int a = need[m.child1[i]], b = need[m.child2[i]];
+            need[i] = (a == 0 && b == 0) ? 1 : (a == b ? a + 1 : (a > b ? a : b));
+        }
+    }
+    uint32_t src(int c) {                 // c is 'L' or 'C': registers its table in program order
+        if (kind[c] == 'L') { m.tc5_leaf_order.push_back(c); return (uint32_t)c; }
+        const uint32_t k = (uint32_t)m.tc5_cherries.size();
+        m.tc5_cherries.push_back(c);
+        m.tc5_cherry_leaves.push_back((uint16_t)(m.child1[c] | (m.child2[c] << 8)));
+        return T5_SRC_CHERRY | k;
+    }
+    void alpha(int i) {                   // leaves alpha_i as the running partial
+        const int c1 = m.child1[i], c2 = m.child2[i];
+        const bool i1 = kind[c1] == 'I', i2 = kind[c2] == 'I';
+        if (!i1 && !i2) {
+            const uint32_t a = src(c1), b = src(c2);
+            ops.push_back((1u << 16) | a | (b << 8)); op_edge.push_back(-1);
+        } else if (i1 != i2) {
+            const int inner = i1 ? c1 : c2, other = i1 ? c2 : c1;
+            msg(inner);
+            ops.push_back((3u << 16) | src(other)); op_edge.push_back(-1);
+        } else {
+            const int first = need[c1] >= need[c2] ? c1 : c2, second = first == c1 ? c2 : c1;
+            msg(first);
+            ops.push_back(4u << 16); op_edge.push_back(-1);
+            if (++sp > m.tc5_max_stack) m.tc5_max_stack = sp;
+            msg(second);
+            ops.push_back(5u << 16); op_edge.push_back(-1);
+            --sp;
+        }
+    }
+    void msg(int c) { alpha(c); ops.push_back(2u << 16); op_edge.push_back(c); }
+};
+
+// Returns nullptr on success.
+inline const char *prepare_tc5_program(ModelHost &m) {
+    m.tc5_steps.clear(); m.tc5_edges.clear(); m.tc5_leaf_order.clear(); m.tc5_cherries.clear(); m.tc5_cherry_leaves.clear();
+    m.tc5_max_stack = 0; m.tc5_start = 0;
+    Tc5Emit e(m);
+    e.classify(m.n - 1);
+    e.alpha(m.n - 1);
+    const std::vector<uint32_t> &ops = e.ops;
+    auto code = [&](size_t i) { return i < ops.size() ? ops[i] >> 16 : 0u; };
+    if (code(0) != 1) return "internal error: tcgen05 program does not begin with a chain start";
+    m.tc5_start = ops[0] & 0xffffu;
+    size_t i = 1;
+    while (code(i) == 2) {
+        uint32_t w = 0;
+        m.tc5_edges.push_back(e.op_edge[i]);
+        ++i;
+        if (code(i) == 3) { w = (ops[i] & 0xffu) | (T5_MUL << 16); ++i; }
+        else if (code(i) == 4) {
+            if (code(i + 1) != 1) return "internal error: tcgen05 program: PUSH not followed by a chain start";
+            w = (ops[i + 1] & 0xffffu) | (T5_PUSH_START << 16);
+            i += 2;
+        } else if (code(i) == 5) { w = T5_POP_MUL << 16; ++i; }
+        else return "internal error: tcgen05 program: a message is neither multiplied nor pushed";
+        m.tc5_steps.push_back(w);
+    }
+    if (!m.tc5_steps.empty()) m.tc5_steps.back() |= T5_END;
+    int n_inner_edges = 0;
+    for (int v = m.nl; v < m.n - 1; ++v) n_inner_edges += e.kind[v] == 'I';
+    if (i != ops.size() || (int)m.tc5_steps.size() != n_inner_edges ||
+        (int)m.tc5_leaf_order.size() + 2 * (int)m.tc5_cherries.size() != m.nl || m.tc5_cherries.size() > 127)
+        return "internal error: tcgen05 step list";
+    return nullptr;
+}
+
 inline void bls_walk(ModelHost &m, int i, uint64_t &lo, uint64_t &hi, int &depth_out) {
     BlsNode e{};
     e.bl = m.bl64[i];
@@ -390,51 +467,7 @@ inline std::string prepare_model(ModelHost &m, int nl, const int16_t *c1, const 
     detail::emit_partial(m, m.n - 1, need, sp);
     m.program.push_back(mk_op(OP_END, 0));
     if ((int)m.gemm_edges.size() != nl - 2) return "internal error: GEMM count";
-    // the same program as one step per GEMM for the tcgen05 path; between two GEMMs the program is one of
-    //   (nothing) | GATHER_MUL l | PUSH GATHER_SET l1 GATHER_MUL l2 | POP_MUL        (see emit_partial)
-    m.tc5_steps.clear(); m.tc5_edges.clear(); m.tc5_leaf_order.clear();
-    {
-        const std::vector<int32_t> &pr = m.program;
-        auto code = [&](size_t i) { return i < pr.size() ? (int)(pr[i] >> 16) : -1; };
-        auto arg = [&](size_t i) { return (int)(pr[i] & 0xffff); };
-        if (code(0) != OP_GATHER_SET || code(1) != OP_GATHER_MUL) return "internal error: program does not start with a cherry";
-        m.tc5_first[0] = arg(0); m.tc5_first[1] = arg(1);
-        m.tc5_leaf_order.push_back(arg(0)); m.tc5_leaf_order.push_back(arg(1));
-        size_t i = 2;
-        while (code(i) == OP_GEMM) {
-            uint32_t w = 0;
-            m.tc5_edges.push_back(m.gemm_edges[arg(i)]);
-            ++i;
-            if (code(i) == OP_GATHER_MUL) {
-                w = (uint32_t)arg(i) | (T5_MUL_LEAF << 16);
-                m.tc5_leaf_order.push_back(arg(i));
-                ++i;
-            } else if (code(i) == OP_PUSH) {
-                if (code(i + 1) != OP_GATHER_SET || code(i + 2) != OP_GATHER_MUL) return "internal error: PUSH not followed by a cherry";
-                w = (uint32_t)arg(i + 1) | ((uint32_t)arg(i + 2) << 8) | (T5_PUSH_CHERRY << 16);
-                m.tc5_leaf_order.push_back(arg(i + 1)); m.tc5_leaf_order.push_back(arg(i + 2));
-                i += 3;
-            } else if (code(i) == OP_POP_MUL) {
-                w = T5_POP_MUL << 16;
-                ++i;
-            }
-            if (code(i) == OP_END) { w |= T5_END; ++i; }
-            m.tc5_steps.push_back(w);
-        }
-        if (m.tc5_steps.empty() && code(i) == OP_END) ++i;      // two leaves: the cherry is the whole tree
-        {
-            int depth = 0, cnt[16] = {0};
-            for (uint32_t w : m.tc5_steps) {
-                const uint32_t post = (w >> 16) & 3u;
-                if (post == T5_PUSH_CHERRY) { if (depth < 16) cnt[depth]++; ++depth; }
-                else if (post == T5_POP_MUL) --depth;
-            }
-            m.tc5_smem_depth = 0;
-            for (int d = 1; d < 16; ++d) if (cnt[d] > cnt[m.tc5_smem_depth]) m.tc5_smem_depth = d;
-        }
-        if (i != pr.size() || (int)m.tc5_steps.size() != nl - 2 || (int)m.tc5_leaf_order.size() != nl)
-            return "internal error: tcgen05 step list";
-    }
+    if (const char *terr = detail::prepare_tc5_program(m)) return terr;
     // BLS program
     uint64_t lo, hi;
     m.bls_prog.clear();
@@ -463,17 +496,15 @@ inline std::string prepare_model(ModelHost &m, int nl, const int16_t *c1, const 
             to_fragment_order(e.P.data() + (size_t)m.gemm_edges[g] * NS * NS, e.pstream.data() + g * NS * NS);
         e.leafPT.resize((size_t)nl * 65 * NS);
         for (int l = 0; l < nl; ++l) to_leaf_table(e.P.data() + (size_t)l * NS * NS, e.leafPT.data() + (size_t)l * 65 * NS);
-        e.pstream32.resize(m.gemm_edges.size() * (size_t)2 * NS * NS);
-        for (size_t g = 0; g < m.gemm_edges.size(); ++g)
-            to_fragment_order_tf32(e.P.data() + (size_t)m.gemm_edges[g] * NS * NS, e.pstream32.data() + g * 2 * NS * NS);
         e.pstream_tc5.resize(m.tc5_edges.size() * (size_t)8192);
         for (size_t st = 0; st < m.tc5_edges.size(); ++st)
             to_tc5_tile(e.P.data() + (size_t)m.tc5_edges[st] * NS * NS, e.pstream_tc5.data() + st * 8192);
         e.leaf_tc5.resize(m.tc5_leaf_order.size() * (size_t)T5_LEAF_FLOATS);
         for (size_t k = 0; k < m.tc5_leaf_order.size(); ++k)
             to_tc5_leaf(e.P.data() + (size_t)m.tc5_leaf_order[k] * NS * NS, e.leaf_tc5.data() + k * T5_LEAF_FLOATS);
-        e.leafPT32.resize(e.leafPT.size());
-        for (size_t i = 0; i < e.leafPT.size(); ++i) e.leafPT32[i] = (float)e.leafPT[i];
+        e.cherry_P.resize(m.tc5_cherries.size() * (size_t)NS * NS);
+        for (size_t k = 0; k < m.tc5_cherries.size(); ++k)
+            std::memcpy(e.cherry_P.data() + k * NS * NS, e.P.data() + (size_t)m.tc5_cherries[k] * NS * NS, sizeof(double) * NS * NS);
     }
     return "";
 }

@@ -18,9 +18,7 @@
 #include "kernels.cuh"
 #include "mle.cuh"
 #include "omega.cuh"
-#include "prune_f32.cuh"
 #include "prune_tc5.cuh"
-#include "prune_tc5h.cuh"
 
 using namespace pcsf;
 
@@ -73,17 +71,13 @@ struct pcsf_model {
     double *d_pstream[2] = {nullptr, nullptr}, *d_leafPT[2] = {nullptr, nullptr};
     double *d_pi[2] = {nullptr, nullptr}, *d_logpi[2] = {nullptr, nullptr};
     double *d_eig[2] = {nullptr, nullptr};   // lambda[64] | SR[4096] | SRinv[4096]
-    float *d_pstream32[2] = {nullptr, nullptr}, *d_leafPT32[2] = {nullptr, nullptr};
-    size_t prune_f32_smem = 0;
-    int prune_f32_nwarp = 8;
     float *d_pstream_tc5[2] = {nullptr, nullptr}, *d_leaf_tc5[2] = {nullptr, nullptr};
+    float *d_cherry_tc5[2] = {nullptr, nullptr};   // [n_cherry][65*65][64] message tables of the edges above cherries (k_build_cherry)
+    uint16_t *d_cherry_leaves = nullptr;
     uint32_t *d_tc5_steps = nullptr;
     float *d_tc5_scratch = nullptr;      // stack spill of k_prune_tc5: [sm_count][2][max_stack][T5_STACK_ENTRY_FLOATS]
     size_t prune_tc5_smem = 0;
     int tc5_nstage = 2, tc5_nlstage = 3;
-    size_t prune_tc5h_smem = 0;          // k_prune_tc5h (16 epilogue warps): experimental, PCSF_TC5_VARIANT=half selects it (slower: see DESIGN.md)
-    int tc5h_nstage = 2, tc5h_nlstage = 3;
-    bool tc5_half = false;
     int32_t *d_program = nullptr;
     BlsInner *d_bls_prog = nullptr;
     float *d_bl = nullptr;
@@ -122,15 +116,19 @@ extern "C" pcsf_status pcsf_model_create(const pcsf_model_desc *d, int device, p
         return fail(PCSF_ERR_INVALID, "pcsf_model_create: null argument or fewer than 2 leaves");
     if (d->nl > PCSF_MAX_LEAVES) return fail(PCSF_ERR_UNSUPPORTED, "more than 128 leaves are not supported");
     pcsf_model *m = new pcsf_model;
+    struct Guard {                       // every early return below releases the handle and what it already owns on the device
+        pcsf_model *m;
+        ~Guard() { if (m) pcsf_model_destroy(m); }
+    } guard{m};
     const double *S[2] = {d->ecm_c, d->ecm_nc}, *f[2] = {d->freq_c, d->freq_nc};
     const std::string err = prepare_model(m->host, d->nl, d->child1, d->child2, d->branch_len, d->branch_len_f64, S, f);
     if (!err.empty()) {
-        delete m;
         return fail(err.find("substition_matrix") != std::string::npos ? PCSF_ERR_NUMERIC : PCSF_ERR_INVALID, err);
     }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
-        delete m;
+        guard.m = nullptr;
+        delete m;                        // nothing on a device yet (and pcsf_model_destroy would call cudaSetDevice)
         return fail(PCSF_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
     }
     m->device = device;
@@ -149,8 +147,6 @@ extern "C" pcsf_status pcsf_model_create(const pcsf_model_desc *d, int device, p
         const EcmHost &e = m->host.ecm[w];
         if ((st = upload(e.pstream.data(), e.pstream.size() * 8, (void **)&m->d_pstream[w]))) return st;
         if ((st = upload(e.leafPT.data(), e.leafPT.size() * 8, (void **)&m->d_leafPT[w]))) return st;
-        if ((st = upload(e.pstream32.data(), e.pstream32.size() * 4, (void **)&m->d_pstream32[w]))) return st;
-        if ((st = upload(e.leafPT32.data(), e.leafPT32.size() * 4, (void **)&m->d_leafPT32[w]))) return st;
         if ((st = upload(e.pstream_tc5.data(), e.pstream_tc5.size() * 4, (void **)&m->d_pstream_tc5[w]))) return st;
         if ((st = upload(e.leaf_tc5.data(), e.leaf_tc5.size() * 4, (void **)&m->d_leaf_tc5[w]))) return st;
         if ((st = upload(e.pi, 64 * 8, (void **)&m->d_pi[w]))) return st;
@@ -163,18 +159,29 @@ extern "C" pcsf_status pcsf_model_create(const pcsf_model_desc *d, int device, p
     }
     if ((st = upload(m->host.program.data(), m->host.program.size() * 4, (void **)&m->d_program))) return st;
     if ((st = upload(m->host.tc5_steps.data(), m->host.tc5_steps.size() * 4, (void **)&m->d_tc5_steps))) return st;
-    CK(cudaMalloc(&m->d_tc5_scratch, (size_t)m->sm_count * 2 * std::max(1, m->host.max_stack) * T5_STACK_ENTRY_FLOATS * 4));
-    prune_tc5_pick_stages(m->host.nl, (int)m->host.tc5_steps.size(), &m->tc5_nstage, &m->tc5_nlstage);
+    CK(cudaMalloc(&m->d_tc5_scratch, (size_t)m->sm_count * 2 * std::max(1, m->host.tc5_max_stack) * T5_STACK_ENTRY_FLOATS * 4));
+    {
+        // cherry message tables: FP64 on the device from the cherry nodes' P and the two leaves' columns, stored as FP32 rows
+        const int nc = (int)m->host.tc5_cherries.size();
+        if ((st = upload(m->host.tc5_cherry_leaves.data(), (size_t)nc * 2, (void **)&m->d_cherry_leaves))) return st;
+        for (int w = 0; w < 2 && nc > 0; ++w) {
+            double *d_cp = nullptr;
+            if ((st = upload(m->host.ecm[w].cherry_P.data(), m->host.ecm[w].cherry_P.size() * 8, (void **)&d_cp))) return st;
+            cudaError_t e = cudaMalloc(&m->d_cherry_tc5[w], (size_t)nc * T5_CHERRY_ROWS * 64 * 4);
+            if (e == cudaSuccess) {
+                k_build_cherry<<<dim3(65, nc), 64>>>(d_cp, m->d_leafPT[w], m->d_cherry_leaves, m->d_cherry_tc5[w]);
+                e = cudaGetLastError();
+                if (e == cudaSuccess) e = cudaDeviceSynchronize();
+            }
+            cudaFree(d_cp);
+            CK(e);
+        }
+    }
+    prune_tc5_pick_stages(m->host.nl, (int)m->host.tc5_steps.size(), (int)m->host.tc5_cherries.size(), &m->tc5_nstage, &m->tc5_nlstage);
     if (const char *e = getenv("PCSF_TC5_NSTAGE")) m->tc5_nstage = std::max(2, std::min(m->tc5_nstage, atoi(e)));
     if (const char *e = getenv("PCSF_TC5_NLSTAGE")) m->tc5_nlstage = std::max(3, std::min(m->tc5_nlstage, atoi(e)));
-    m->prune_tc5_smem = prune_tc5_smem_bytes(m->host.nl, (int)m->host.tc5_steps.size(), m->tc5_nstage, m->tc5_nlstage);
+    m->prune_tc5_smem = prune_tc5_smem_bytes(m->host.nl, (int)m->host.tc5_steps.size(), (int)m->host.tc5_cherries.size(), m->tc5_nstage, m->tc5_nlstage);
     CK(cudaFuncSetAttribute(k_prune_tc5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->prune_tc5_smem));
-    prune_tc5h_pick_stages(m->host.nl, (int)m->host.tc5_steps.size(), &m->tc5h_nstage, &m->tc5h_nlstage);
-    if (const char *e = getenv("PCSF_TC5_NSTAGE")) m->tc5h_nstage = std::max(2, std::min(m->tc5h_nstage, atoi(e)));
-    if (const char *e = getenv("PCSF_TC5_NLSTAGE")) m->tc5h_nlstage = std::max(3, std::min(m->tc5h_nlstage, atoi(e)));
-    m->prune_tc5h_smem = prune_tc5h_smem_bytes(m->host.nl, (int)m->host.tc5_steps.size(), m->tc5h_nstage, m->tc5h_nlstage);
-    CK(cudaFuncSetAttribute(k_prune_tc5h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->prune_tc5h_smem));
-    if (const char *e = getenv("PCSF_TC5_VARIANT")) m->tc5_half = strcmp(e, "half") == 0;
     if ((st = upload(m->host.bls_inner.data(), m->host.bls_inner.size() * sizeof(BlsInner), (void **)&m->d_bls_prog))) return st;
     if ((st = upload(m->host.bl.data(), m->host.bl.size() * 4, (void **)&m->d_bl))) return st;
     {
@@ -201,18 +208,11 @@ extern "C" pcsf_status pcsf_model_create(const pcsf_model_desc *d, int device, p
         return fail(PCSF_ERR_UNSUPPORTED, "tree needs more shared memory than one SM has (stack depth " +
                                               std::to_string(m->host.max_stack) + ")");
     }
-    m->prune_f32_nwarp = PF_MAX_NWARP;
-    if (const char *e = getenv("PCSF_PRUNE_F32_NWARP")) m->prune_f32_nwarp = std::max(1, std::min(PF_MAX_NWARP, atoi(e)));
-    while (m->prune_f32_nwarp > 4 &&
-           prune_f32_smem_bytes(m->host.nl, (int)m->host.program.size(), m->host.max_stack, m->prune_f32_nwarp) > 227 * 1024)
-        m->prune_f32_nwarp -= 2;
-    m->prune_f32_smem = prune_f32_smem_bytes(m->host.nl, (int)m->host.program.size(), m->host.max_stack, m->prune_f32_nwarp);
-    if (m->prune_f32_smem <= 227 * 1024)
-        CK(cudaFuncSetAttribute(k_prune_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->prune_f32_smem));
     CK(cudaFuncSetAttribute(k_prune<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->prune_smem));
     CK(cudaFuncSetAttribute(k_prune<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->prune_smem));
     CK(cudaFuncSetAttribute(k_bls, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             std::max(1, m->host.bls_depth) * BLS_THREADS * 8));
+    guard.m = nullptr;
     *out = m;
     return PCSF_OK;
 }
@@ -221,11 +221,11 @@ extern "C" void pcsf_model_destroy(pcsf_model *m) {
     if (!m) return;
     cudaSetDevice(m->device);
     for (int w = 0; w < 2; ++w) {
-        cudaFree(m->d_pstream[w]); cudaFree(m->d_leafPT[w]); cudaFree(m->d_pstream32[w]); cudaFree(m->d_leafPT32[w]); cudaFree(m->d_pstream_tc5[w]); cudaFree(m->d_leaf_tc5[w]); cudaFree(m->d_pi[w]); cudaFree(m->d_logpi[w]);
+        cudaFree(m->d_pstream[w]); cudaFree(m->d_leafPT[w]); cudaFree(m->d_cherry_tc5[w]); cudaFree(m->d_pstream_tc5[w]); cudaFree(m->d_leaf_tc5[w]); cudaFree(m->d_pi[w]); cudaFree(m->d_logpi[w]);
         cudaFree(m->d_eig[w]);
     }
     cudaFree(m->d_program); cudaFree(m->d_bls_prog); cudaFree(m->d_bl); cudaFree(m->d_gemm_edges);
-    cudaFree(m->d_bad); cudaFree(m->d_nuniq); cudaFree(m->d_tc5_steps); cudaFree(m->d_tc5_scratch);
+    cudaFree(m->d_bad); cudaFree(m->d_nuniq); cudaFree(m->d_tc5_steps); cudaFree(m->d_tc5_scratch); cudaFree(m->d_cherry_leaves);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     if (m->h2d_stream) cudaStreamDestroy(m->h2d_stream);
@@ -269,7 +269,7 @@ static inline uint32_t next_pow2(uint64_t x) {
 
 // dedup + prune for one window space of `nwin` local windows; results land in m->pidx (pattern id per
 // window), m->logz / m->anc (per pattern); *d_nuniq_slot receives the pattern count.
-static pcsf_status dedup_and_prune(pcsf_model *m, const WinSpace &ws, uint32_t nwin, bool dedup, bool want_anc, int prec /* 0 FP64 DMMA, 1 split-TF32 mma.sync, 2 tcgen05 */,
+static pcsf_status dedup_and_prune(pcsf_model *m, const WinSpace &ws, uint32_t nwin, bool dedup, bool want_anc, int prec /* 0 FP64 DMMA, 2 tcgen05 */,
                                    uint32_t *d_nuniq_slot, uint32_t *d_pattern_out, int64_t out_base,
                                    cudaStream_t st, float *ms_hash, float *ms_dedup, float *ms_prune) {
     const int TB = 256;
@@ -305,7 +305,7 @@ static pcsf_status dedup_and_prune(pcsf_model *m, const WinSpace &ws, uint32_t n
         CK(m->bsums.reserve((size_t)(nsb + 1) * 4));
         CK(cudaMemsetAsync(m->table.p, 0xFF, (size_t)T * 4, st));
         CK(cudaMemsetAsync(m->slotmin.p, 0xFF, (size_t)T * 4, st));
-        m->launches += 5; k_insert<<<nblk, TB, 0, st>>>(m->klo.as<uint64_t>(), m->khi.as<uint64_t>(), nwin, m->table.as<uint32_t>(), T - 1,
+        m->launches += 5; k_insert<<<nblk, TB, 0, st>>>(ws, m->klo.as<uint64_t>(), m->khi.as<uint64_t>(), nwin, m->table.as<uint32_t>(), T - 1,
                                       m->slot.as<uint32_t>(), m->slotmin.as<uint32_t>());
         k_resolve<<<nblk, TB, 0, st>>>(nwin, m->slot.as<uint32_t>(), m->slotmin.as<uint32_t>(), m->flag.as<uint32_t>());
         k_scan_blocks<<<nsb, SCAN_THREADS, 0, st>>>(m->flag.as<uint32_t>(), nwin, m->bsums.as<uint32_t>());
@@ -327,55 +327,25 @@ static pcsf_status dedup_and_prune(pcsf_model *m, const WinSpace &ws, uint32_t n
         ta.n_unique = d_nuniq_slot;
         ta.steps = m->d_tc5_steps;
         ta.n_steps = (int)m->host.tc5_steps.size();
-        ta.max_stack = m->host.max_stack;
-        ta.first0 = m->host.tc5_first[0];
-        ta.first1 = m->host.tc5_first[1];
-        ta.nstage = m->tc5_half ? m->tc5h_nstage : m->tc5_nstage;
-        ta.nlstage = m->tc5_half ? m->tc5h_nlstage : m->tc5_nlstage;
+        ta.max_stack = m->host.tc5_max_stack;
+        ta.start = m->host.tc5_start;
+        ta.n_leaf_tabs = (int)m->host.tc5_leaf_order.size();
+        ta.n_cherry = (int)m->host.tc5_cherries.size();
+        ta.cherry_leaves = m->d_cherry_leaves;
+        ta.nstage = m->tc5_nstage;
+        ta.nlstage = m->tc5_nlstage;
         ta.scratch = m->d_tc5_scratch;
         for (int w = 0; w < 2; ++w) {
             ta.pstream[w] = m->d_pstream_tc5[w];
             ta.leaftab[w] = m->d_leaf_tc5[w];
+            ta.cherrytab[w] = m->d_cherry_tc5[w];
             ta.pi[w] = m->d_pi[w];
             ta.logz[w] = m->logz.as<double>() + (size_t)w * nwin;
         }
         const uint32_t mp = (nwin + 255) / 256;
         const unsigned gridt = std::min<uint32_t>((uint32_t)m->sm_count, std::max<uint32_t>(1u, mp));
         m->launches++;
-        if (m->tc5_half) k_prune_tc5h<<<gridt, T5H_THREADS, m->prune_tc5h_smem, st>>>(ta);
-        else k_prune_tc5<<<gridt, T5_THREADS, m->prune_tc5_smem, st>>>(ta);
-        CK(cudaGetLastError());
-        if (m->timing) {
-            CK(cudaEventRecord(m->ev[3], st));
-            CK(cudaEventSynchronize(m->ev[3]));
-            float t;
-            CK(cudaEventElapsedTime(&t, m->ev[0], m->ev[1])); *ms_hash += t;
-            CK(cudaEventElapsedTime(&t, m->ev[1], m->ev[2])); *ms_dedup += t;
-            CK(cudaEventElapsedTime(&t, m->ev[2], m->ev[3])); *ms_prune += t;
-        }
-        return PCSF_OK;
-    }
-    if (prec == 1) {
-        PruneF32Args fa{};
-        fa.ws = ws;
-        fa.uniq = m->uniq.as<uint32_t>();
-        fa.n_unique = d_nuniq_slot;
-        fa.program = m->d_program;
-        fa.n_ops = (int)m->host.program.size();
-        fa.n_gemm = (int)m->host.gemm_edges.size();
-        fa.max_stack = m->host.max_stack;
-        fa.stagger_ns = m->stagger_ns;
-        fa.nwarp = m->prune_f32_nwarp;
-        for (int w = 0; w < 2; ++w) {
-            fa.pstream[w] = m->d_pstream32[w];
-            fa.leafPT[w] = m->d_leafPT32[w];
-            fa.pi[w] = m->d_pi[w];
-            fa.logz[w] = m->logz.as<double>() + (size_t)w * nwin;
-        }
-        const uint32_t twf = (uint32_t)m->prune_f32_nwarp * 16;
-        const uint32_t mt = (nwin + twf - 1) / twf;
-        const unsigned gridf = std::min<uint32_t>((uint32_t)m->sm_count, std::max<uint32_t>(1u, mt));
-        m->launches++; k_prune_f32<<<gridf, (m->prune_f32_nwarp + 1) * 32, m->prune_f32_smem, st>>>(fa);
+        k_prune_tc5<<<gridt, T5_THREADS, m->prune_tc5_smem, st>>>(ta);
         CK(cudaGetLastError());
         if (m->timing) {
             CK(cudaEventRecord(m->ev[3], st));
@@ -468,8 +438,8 @@ extern "C" pcsf_status pcsf_tracks_device(pcsf_model *m, const uint8_t *d_seqs, 
     if (!m || L < 0 || ld < L || (L > 0 && !d_seqs)) return fail(PCSF_ERR_INVALID, "pcsf_tracks: bad argument");
     if ((flags & PCSF_TRACKS_SCORES) && L > 2 && (!d_plus || !d_minus)) return fail(PCSF_ERR_INVALID, "plus/minus required");
     if ((flags & PCSF_TRACKS_BLS) && L > 0 && !d_bls) return fail(PCSF_ERR_INVALID, "bls required");
-    if ((flags & PCSF_TRACKS_FP32) && m->prune_f32_smem > 227 * 1024)
-        return fail(PCSF_ERR_UNSUPPORTED, "tree too deep for the FP32-class tensor path");
+    if ((flags & PCSF_TRACKS_TC5) && m->prune_tc5_smem > 227 * 1024)
+        return fail(PCSF_ERR_UNSUPPORTED, "tree too large for the tcgen05 path's shared-memory budget");
     CK(cudaSetDevice(m->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     m->last = pcsf_tracks_stats{};
@@ -534,9 +504,12 @@ extern "C" pcsf_status pcsf_tracks_device(pcsf_model *m, const uint8_t *d_seqs, 
             if (seg) {
                 const int64_t s0 = c == 0 ? 0 : seg_end(c - 1), s1 = seg_end(c);
                 CK(cudaStreamWaitEvent(st, m->ev_h2d[c], 0));
-                if (s1 > s0 || s1 == L) {
-                    if (s1 > s0 || c + 1 == nchunks) { if ((rc = run_pack_segment(m, d_seqs, ld, s0, s1, s1 == L, st))) return rc; }
-                    if ((flags & PCSF_TRACKS_BLS) && s1 > s0) {
+                // An empty segment (s1 == s0: the previous chunk's halo already reached L) has nothing to pack: the segment that
+                // reached L ran with last = true and wrote the padding columns.  Packing again from s0 = L would start at an
+                // address that is not 16-byte aligned whenever L % 16 != 0 and run into the next species' row.
+                if (s1 > s0) {
+                    if ((rc = run_pack_segment(m, d_seqs, ld, s0, s1, s1 == L, st))) return rc;
+                    if (flags & PCSF_TRACKS_BLS) {
                         if ((rc = run_bls_segment(m, s0, s1, d_bls, st))) return rc;
                         if (m->h_bls) {
                             CK(cudaEventRecord(m->ev_chunk, st));
@@ -547,7 +520,7 @@ extern "C" pcsf_status pcsf_tracks_device(pcsf_model *m, const uint8_t *d_seqs, 
                 }
             }
             WinSpace ws{m->codes.as<uint8_t>(), m->codes_ld, m->host.nl, 0, c0, nullptr};
-            if ((rc = dedup_and_prune(m, ws, nwin, !(flags & PCSF_TRACKS_NO_DEDUP), false, (flags & PCSF_TRACKS_TC5) ? 2 : (flags & PCSF_TRACKS_FP32) ? 1 : 0, m->d_nuniq + c, d_pattern_index,
+            if ((rc = dedup_and_prune(m, ws, nwin, !(flags & PCSF_TRACKS_NO_DEDUP), false, (flags & PCSF_TRACKS_TC5) ? 2 : 0, m->d_nuniq + c, d_pattern_index,
                                       2 * c0, st, &m->last.ms_hash, &m->last.ms_dedup, &m->last.ms_prune)))
                 return rc;
             if (m->timing) CK(cudaEventRecord(m->ev[0], st));
@@ -699,7 +672,18 @@ extern "C" pcsf_status pcsf_score_msa(pcsf_model *m, pcsf_strategy strategy, int
         if ((rc = run_bls(m, Ltot, 1, d_blraw, st))) return rc;
     }
     WinSpace ws{m->codes.as<uint8_t>(), m->codes_ld, nl, 1, 0, reinterpret_cast<const uint32_t *>(mb + o_win)};
-    if (strategy == PCSF_STRATEGY_FIXED) {
+    if (!phylo && !anc) {
+        // nothing but the branch length score is asked for: the reference does not call run() at all then (score_msa.hpp:112),
+        // whatever the strategy — no fit, and no way for a failing fit to turn the batch into an error
+        if (bls) {
+            CK(m->perwin.reserve(64));
+            k_aln_sums<<<(n_aln + 127) / 128, 128, 0, st>>>(n_aln, reinterpret_cast<const int64_t *>(mb + o_ws),
+                                                           reinterpret_cast<const int64_t *>(mb + o_cs),
+                                                           reinterpret_cast<const int64_t *>(mb + o_len), m->perwin.as<double>(),
+                                                           0, d_blraw, m->host.bls_all, nullptr, nullptr, d_bls);
+            CK(cudaGetLastError());
+        }
+    } else if (strategy == PCSF_STRATEGY_FIXED) {
         CK(m->perwin.reserve((size_t)std::max<int64_t>(nwin, 1) * 32));
         if (nwin > 0) {
             float t0 = 0, t1 = 0, t2 = 0;

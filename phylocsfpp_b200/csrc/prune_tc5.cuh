@@ -1,17 +1,23 @@
 // prune_tc5.cuh — k_prune_tc5: Felsenstein pruning on the 5th-generation tensor cores (tcgen05.mma kind::tf32,
-// accumulators and the A operand in TMEM, P tiles and leaf tables streamed by bulk TMA).  FP32-class arithmetic with
-// per-window log-scaling; the FP64 DMMA kernel (k_prune) stays the parity anchor.
+// accumulators and the A operand in TMEM, P tiles and leaf tables streamed by bulk TMA, cherry messages gathered from
+// L2-resident tables).  FP32-class arithmetic with per-window log-scaling; the FP64 DMMA kernel (k_prune) stays the parity anchor.
 //
-// Formulation (ensure_alpha, fixed_lik.hpp:125-164).  For 128 codon windows at a time every INNER edge c -> parent is
-// one GEMM  D[w][a] = sum_b A[w][b] * P_c[a][b]  on the tensor core (M = 128 windows, K = 64 child states):
+// Formulation (ensure_alpha, fixed_lik.hpp:125-164).  For 128 codon windows at a time every edge above a NON-CHERRY inner
+// node c is one GEMM  D[w][a] = sum_b A[w][b] * P_c[a][b]  on the tensor core (M = 128 windows, K = 64 child states):
 // A = alpha_c split into TF32 hi + lo (per-window power-of-two normalised, the exponent kept as an integer);
 // B = [hi(P_c) | lo(P_c)] side by side (N = 128): per k-step one N = 128 MMA with hi(A) gives hi*hi | hi*lo and one
-// N = 64 MMA with lo(A) adds lo*hi, in FP32 accumulators; msg = D[:, 0:64] + D[:, 64:128] (~2^-21 per product).  One MMA
-// instruction has a ~64-cycle floor whatever its N <= 128 (tools/tc5_probe.cu), so the side-by-side layout is what makes
-// two instructions per k-step enough; shared-memory bandwidth (B reads + leaf gathers) is the co-bottleneck.
+// N = 64 MMA with lo(A) adds lo*hi, in FP32 accumulators; msg = D[:, 0:64] + D[:, 64:128] (~2^-21 per product).  A TS-form MMA
+// reads its 4 KB A slab from TMEM at 64 B/clk, i.e. ~64 cycles whatever its N <= 128 (tools/tc5_probe.cu), so the
+// side-by-side layout is what makes two instructions per k-step enough.
 // LEAF edges are not GEMMs: the message of a leaf with codon x is column x of P_l (all ones for a gap/N codon, the row
 // sums of fixed_lik.hpp:111-118).  The epilogue threads gather it from a 17 KB per-leaf table that TMA streams into shared
 // memory in program order — and they do so WHILE their GEMM runs, so leaves cost no tensor time and no latency.
+// CHERRY edges are not GEMMs either (round 2): the message of the edge above a node whose two children are leaves depends only on
+// the two codons, P_c . (P_l[:, x] * P_r[:, y]), 65 x 65 rows of 64 floats tabulated once per model in FP64 (k_build_cherry) and
+// kept in global memory (1.08 MB per cherry and ECM: L2 resident).  Every epilogue warp copies the 32 rows of its own windows
+// with 16-byte cp.async (sixteen lanes per 256-byte row: full sectors) into a private, XOR-swizzled 8 KB staging area one
+// cherry ahead of the program, and each thread then reads its own row without bank conflicts.  That removes 17 of 56 GEMMs,
+// 34 of 58 leaf gathers and half of the stack pushes for 58mammals (28 of 98, 56 of 100 for 100vertebrates).
 //
 // One persistent CTA per SM works on a PAIR of 128-window tiles (chains X and Y) that share both TMA rings: while the
 // tensor core runs chain Y's GEMM of step g, chain X's epilogue turns D_g into A_{g+1} (and vice versa).
@@ -22,9 +28,9 @@
 //   warp 10     TMA producer, leaf tables (17 KB each, up to 6 stages: both chains read every table, so a stage lives
 //               until the trailing chain has used it)
 // The producer warpgroup gives its registers to the epilogue warpgroups (setmaxnreg 40 / 232).
-// Waiting sibling partials (stack depth = Strahler number - 1) spill to an L2-resident scratch in global memory, every
-// thread only ever touching its own column: the push is issued after the next A has been handed to the tensor core, the
-// pop is prefetched while the GEMM runs, so neither is on the critical path.
+// Waiting sibling partials (stack depth = Strahler number over the non-cherry inner nodes - 1) spill to an L2-resident scratch
+// in global memory, every thread only ever touching its own column: the push is issued after the next A has been handed to
+// the tensor core, the pop is prefetched while the GEMM runs, so neither is on the critical path.
 #pragma once
 
 #include "kernels.cuh"
@@ -45,29 +51,66 @@ struct PruneTc5Args {
     const uint32_t *n_unique;
     const uint32_t *steps;
     int n_steps, max_stack;
-    int first0, first1;          // the cherry the program starts with
+    uint32_t start;              // src1 | src2 << 8: the chain start the program begins with
+    int n_leaf_tabs, n_cherry;
     int nstage, nlstage;         // ring depths
     const float *pstream[2];     // [n_steps][8192]
-    const float *leaftab[2];     // [nl][T5_LEAF_FLOATS], program order
+    const float *leaftab[2];     // [n_leaf_tabs][T5_LEAF_FLOATS], program order
+    const float *cherrytab[2];   // [n_cherry][T5_CHERRY_ROWS][64], program order
+    const uint16_t *cherry_leaves;   // [n_cherry] left leaf | right leaf << 8
     const double *pi[2];
     double *logz[2];
     float *scratch;              // [grid][2][max_stack][T5_STACK_ENTRY_FLOATS]
 };
 
-__host__ __device__ inline size_t prune_tc5_smem_bytes(int nl, int n_steps, int nstage, int nlstage) {
+constexpr int T5_CHERRY_STAGE_BYTES = 32 * 256;     // per epilogue warp: the rows of its 32 windows
+
+__host__ __device__ inline size_t prune_tc5_smem_bytes(int nl, int n_steps, int n_cherry, int nstage, int nlstage) {
     size_t b = (size_t)nstage * T5_TILE_BYTES + (size_t)nlstage * T5_LEAF_BYTES;
+    b += (size_t)8 * T5_CHERRY_STAGE_BYTES;                 // cherry row staging
     b += (size_t)2 * nl * 128;                              // leaf codon ids of both tiles
     b += (size_t)(((n_steps + 1) * 4 + 15) / 16) * 16;      // steps
+    b += (size_t)(((n_cherry + 1) * 2 + 15) / 16) * 16;     // cherry leaves
     b += 2 * 64 * 8;                                        // pi
     b += 32 * 8;                                            // mbarriers + TMEM base (2*3 + 2*6 + 4 + 2 barriers)
     return b;
 }
 // Deepest rings that fit into one SM's shared memory.
-inline void prune_tc5_pick_stages(int nl, int n_steps, int *nstage, int *nlstage) {
+inline void prune_tc5_pick_stages(int nl, int n_steps, int n_cherry, int *nstage, int *nlstage) {
     *nstage = T5_MAX_NSTAGE; *nlstage = T5_MAX_NLSTAGE;
-    while (prune_tc5_smem_bytes(nl, n_steps, *nstage, *nlstage) > 227 * 1024 && *nlstage > 3) --*nlstage;
-    while (prune_tc5_smem_bytes(nl, n_steps, *nstage, *nlstage) > 227 * 1024 && *nstage > 2) --*nstage;
+    while (prune_tc5_smem_bytes(nl, n_steps, n_cherry, *nstage, *nlstage) > 227 * 1024 && *nlstage > 4) --*nlstage;
+    while (prune_tc5_smem_bytes(nl, n_steps, n_cherry, *nstage, *nlstage) > 227 * 1024 && *nstage > 2) --*nstage;
+    while (prune_tc5_smem_bytes(nl, n_steps, n_cherry, *nstage, *nlstage) > 227 * 1024 && *nlstage > 3) --*nlstage;
 }
+
+// Cherry tables: T[k][x * 65 + y][a] = sum_b P_c[a][b] * u_x[b] * v_y[b] with u_x = P_l[:, x], v_y = P_r[:, y] (all ones for
+// index 64, the gap/N codon — the leaf rule of this path), FP64 accumulation, FP32 storage.  grid (65, n_cherry), 64 threads.
+__global__ void __launch_bounds__(64) k_build_cherry(const double *__restrict__ cherry_P, const double *__restrict__ leafPT,
+                                                     const uint16_t *__restrict__ cherry_leaves, float *__restrict__ tab) {
+    __shared__ double u[64];
+    __shared__ double v[65][64];
+    const int k = blockIdx.y, x = blockIdx.x, a = threadIdx.x;
+    const int l = cherry_leaves[k] & 0xff, r = cherry_leaves[k] >> 8;
+    u[a] = x < 64 ? leafPT[((size_t)l * 65 + x) * 64 + a] : 1.0;
+    for (int y = 0; y < 65; ++y) v[y][a] = y < 64 ? leafPT[((size_t)r * 65 + y) * 64 + a] : 1.0;
+    __syncthreads();
+    double pa[64];
+#pragma unroll
+    for (int b = 0; b < 64; ++b) pa[b] = cherry_P[(size_t)k * 4096 + a * 64 + b] * u[b];
+    float *out = tab + ((size_t)k * T5_CHERRY_ROWS + (size_t)x * 65) * 64 + a;
+    for (int y = 0; y < 65; ++y) {
+        double s = 0.0;
+#pragma unroll
+        for (int b = 0; b < 64; ++b) s += pa[b] * v[y][b];
+        out[(size_t)y * 64] = (float)s;
+    }
+}
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args a) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -75,8 +118,10 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
     const uint32_t T5_NSTAGE = a.nstage, T5_NLSTAGE = a.nlstage;
     unsigned char *stage_buf = sp_; sp_ += (size_t)T5_NSTAGE * T5_TILE_BYTES;
     unsigned char *leaf_buf = sp_; sp_ += (size_t)T5_NLSTAGE * T5_LEAF_BYTES;
+    unsigned char *cherry_buf = sp_; sp_ += (size_t)8 * T5_CHERRY_STAGE_BYTES;
     uint8_t *ids = sp_; sp_ += (size_t)2 * a.ws.nl * 128;
     uint32_t *steps = reinterpret_cast<uint32_t *>(sp_); sp_ += (size_t)(((a.n_steps + 1) * 4 + 15) / 16) * 16;
+    uint16_t *cherry_leaves = reinterpret_cast<uint16_t *>(sp_); sp_ += (size_t)(((a.n_cherry + 1) * 2 + 15) / 16) * 16;
     double *s_pi = reinterpret_cast<double *>(sp_); sp_ += 2 * 64 * 8;
     uint64_t *full = reinterpret_cast<uint64_t *>(sp_);
     uint64_t *empty = full + T5_MAX_NSTAGE;
@@ -101,6 +146,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
     }
     if (warp == 8) { tc5::tmem_alloc(tmem_base_slot, 512); tc5::tmem_relinquish(); }
     for (int i = tid; i < a.n_steps; i += blockDim.x) steps[i] = a.steps[i];
+    for (int i = tid; i < a.n_cherry; i += blockDim.x) cherry_leaves[i] = a.cherry_leaves[i];
     for (int i = tid; i < 128; i += blockDim.x) s_pi[i] = a.pi[i >> 6][i & 63];
     tc5::fence_before_sync();
     __syncthreads();
@@ -131,7 +177,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
                 uint32_t use = 0;
                 for (uint32_t pair = blockIdx.x; pair < npairs; pair += gridDim.x)
                     for (int m = 0; m < 2; ++m)
-                        for (int k = 0; k < a.ws.nl; ++k, ++use) {
+                        for (int k = 0; k < a.n_leaf_tabs; ++k, ++use) {
                             const uint32_t st = use % T5_NLSTAGE;
                             mbar_wait(lempty + st, ((use / T5_NLSTAGE) & 1) ^ 1);
                             mbar_arrive_expect_tx(lfull + st, T5_LEAF_BYTES);
@@ -214,6 +260,48 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
             ++luse;
         };
 
+        // Cherry rows.  The warp owns a 32-row x 256-byte staging area; chunk ch (16 bytes) of row rr sits at chunk position
+        // (ch & 8) | ((ch ^ rr) & 7): the sixteen lanes that copy one row write two full 128-byte lines, and the eight threads of a
+        // quarter warp that later read chunk j of their OWN rows (LDS.128) hit eight different bank groups.
+        unsigned char *cstage = cherry_buf + (size_t)warp * T5_CHERRY_STAGE_BYTES;
+        const uint32_t cstage_s = tc5::smem_addr(cstage);
+        int ck = 0;                        // cherry (program order) whose rows are in flight / staged
+        auto prefetch_cherry = [&](int m, int k) {
+            const uint32_t cl = cherry_leaves[k];
+            const uint32_t myrow = (uint32_t)myids[(cl & 0xffu) * 128] * 65u + (uint32_t)myids[(cl >> 8) * 128];
+            const float *tab = a.cherrytab[m] + (size_t)k * ((size_t)T5_CHERRY_ROWS * 64);
+            const int half = lane >> 4, ch = lane & 15;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int rr = 2 * i + half;                      // the window (row of the staging area) this lane copies a chunk of
+                const uint32_t row = __shfl_sync(0xffffffffu, myrow, rr);
+                cp_async_16(cstage_s + rr * 256 + (((ch & 8) | ((ch ^ rr) & 7)) << 4), tab + (size_t)row * 64 + ch * 4);
+            }
+            cp_async_commit();
+        };
+        // L (= or *=) the staged cherry message of this thread's window; then starts the copy of the next cherry of the program
+        // (same ECM, or the other ECM's first one; the next pair's first one is started once its leaf ids are known)
+        auto take_cherry = [&](float (&L)[64], bool mul, int m) {
+            cp_async_wait_all();
+            __syncwarp();
+            const float4 *row = reinterpret_cast<const float4 *>(cstage + lane * 256);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float4 v = row[(j & 8) | ((j ^ lane) & 7)];
+                if (mul) { L[4 * j] *= v.x; L[4 * j + 1] *= v.y; L[4 * j + 2] *= v.z; L[4 * j + 3] *= v.w; }
+                else { L[4 * j] = v.x; L[4 * j + 1] = v.y; L[4 * j + 2] = v.z; L[4 * j + 3] = v.w; }
+            }
+            __syncwarp();
+            // the copy of the program's next cherry starts right away: it needs a whole step of lead time (issuing it only after
+            // this step's hand-over was measured 40 % slower at 8 Mi columns: the rows then come from DRAM as often as from L2)
+            if (++ck < a.n_cherry) prefetch_cherry(m, ck);
+            else { ck = 0; if (m == 0) prefetch_cherry(1, 0); }
+        };
+        auto fetch = [&](float (&L)[64], uint32_t src, bool mul, int m) {
+            if (src & T5_SRC_CHERRY) take_cherry(L, mul, m);
+            else gather(L, (int)src, mul);
+        };
+
 #ifdef PCSF_TC5_TRACE
         long long t_ids = 0, t_seq = 0, t_pro = 0, t_begin = clock64();
 #endif
@@ -244,6 +332,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
                             myids[(s0 + k) * 128] = (uint8_t)(strand ? codon_minus(v[k][0], v[k][1], v[k][2]) : codon_plus(v[k][0], v[k][1], v[k][2]));
                 }
             }
+            if (a.n_cherry > 0) prefetch_cherry(0, 0);
 #ifdef PCSF_TC5_TRACE
             t_ids += clock64() - tt0;
 #endif
@@ -253,8 +342,8 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
 #ifdef PCSF_TC5_TRACE
                 long long tt1 = clock64();
 #endif
-                gather(R, a.first0, false);
-                gather(R, a.first1, true);
+                fetch(R, a.start & 0xffu, false, m);
+                fetch(R, (a.start >> 8) & 0xffu, true, m);
 #ifdef PCSF_TC5_TRACE
                 long long tt2 = clock64();
                 t_pro += tt2 - tt1;
@@ -306,14 +395,15 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
 #endif
                     T5_TRACE(c, s, 0);
                     // ---- while the GEMM runs: what the program multiplies in before the next GEMM — leaf messages from
-                    // their shared-memory tables, or the waiting sibling partial from the stack
+                    // their shared-memory tables, cherry messages from the staged table rows, or the waiting sibling partial
+                    // from the stack
                     float L[64];
                     int Epop = 0;
-                    if (post == T5_MUL_LEAF) {
-                        gather(L, (int)(step & 0xffu), false);
-                    } else if (post == T5_PUSH_CHERRY) {
-                        gather(L, (int)(step & 0xffu), false);
-                        gather(L, (int)((step >> 8) & 0xffu), true);
+                    if (post == T5_MUL) {
+                        fetch(L, step & 0xffu, false, m);
+                    } else if (post == T5_PUSH_START) {
+                        fetch(L, step & 0xffu, false, m);
+                        fetch(L, (step >> 8) & 0xffu, true, m);
                     } else if (post == T5_POP_MUL) {
                         --sp;
                         const float4 *e4 = reinterpret_cast<const float4 *>(stk + (size_t)sp * T5_STACK_ENTRY_FLOATS);
@@ -329,7 +419,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
                     T5_TRACE(c, s, 2);
                     tc5::fence_after_sync();
                     const uint32_t dreg = lane_base + ((use & 1) ^ 1) * 128;     // D_s; A_{s+1} overwrites it in place
-                    if (post == T5_PUSH_CHERRY || s + 1 == a.n_steps) {
+                    if (post == T5_PUSH_START || s + 1 == a.n_steps) {
                         // the message itself is needed (pushed onto the stack / dotted with pi): load all of it
                         {
                             uint32_t x0[32], y0[32], x1[32], y1[32];
@@ -348,17 +438,17 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
                                 R[i] = v0.x; R[i + 1] = v0.y; R[32 + i] = v1.x; R[32 + i + 1] = v1.y;
                             }
                         }
-                        if (post == T5_PUSH_CHERRY) {
-                            // the next GEMM's input is the cherry (already in L): hand it over first, then push the message
+                        if (post == T5_PUSH_START) {
+                            // the next GEMM's input is the new chain's start (already in L): hand it over first, then push the message
                             const int Epush = E;
                             E = 0;
                             split_and_arrive(L, dreg);
-                            float4 *e4 = reinterpret_cast<float4 *>(stk + (size_t)sp * T5_STACK_ENTRY_FLOATS);
+                                        float4 *e4 = reinterpret_cast<float4 *>(stk + (size_t)sp * T5_STACK_ENTRY_FLOATS);
 #pragma unroll
                             for (int j = 0; j < 16; ++j) __stcg(e4 + j * 128 + t, make_float4(R[4 * j], R[4 * j + 1], R[4 * j + 2], R[4 * j + 3]));
                             __stcg(reinterpret_cast<int *>(stk + (size_t)sp * T5_STACK_ENTRY_FLOATS + 8192) + t, Epush);
                             ++sp;
-                        } else if (post == T5_MUL_LEAF || post == T5_POP_MUL) {
+                        } else if (post == T5_MUL || post == T5_POP_MUL) {
 #pragma unroll
                             for (int i = 0; i < 64; i += 2) {
                                 const float2 v = __fmul2_rn(make_float2(R[i], R[i + 1]), make_float2(L[i], L[i + 1]));
@@ -373,7 +463,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
                         // that previous maximum keeps the new A below 2, and how far below is corrected one step later.  Without
                         // a separate max pass the scale is folded into the combine (streaming the TMEM loads in two halves was measured slower:
                         // a second tcgen05.wait::ld round trip costs more than the overlap gains, 114 against 97 ms).
-                        const bool mul = post == T5_MUL_LEAF || post == T5_POP_MUL;
+                        const bool mul = post == T5_MUL || post == T5_POP_MUL;
                         const int e = amax_prev > 0.f ? (int)((__float_as_uint(amax_prev) >> 23) & 0xff) - 127 : 0;
                         const float sc = __uint_as_float((uint32_t)(127 - e) << 23);
                         const float2 sc2 = make_float2(sc, sc);
@@ -422,7 +512,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
                         tc5::fence_before_sync();
                         mbar_arrive(a_ready + 2 * c + 1);
                         amax_prev = amax;
-                    }
+                            }
                     T5_TRACE(c, s, 3);
                 }
                 // z = pi . alpha_root (fixed_lik.hpp:159-163), log z with the exponents taken out so far

@@ -187,7 +187,9 @@ private:
     void scan_range(size_t from, size_t to, std::vector<BlockMeta> &out, std::set<std::string> &unres) const {
         // blocks whose "a " line starts in [from, to)
         size_t pos = from;
-        auto at_block = [&](size_t p) { return p + 1 < size_ && mem_[p] == 'a' && mem_[p + 1] == ' ' && (p == 0 || mem_[p - 1] == '\n'); };
+        // the reference takes any line whose first character is 'a' as a block start (get_char, parallel_file_reader.hpp:476): bare "a",
+        // "a\tscore=..." and "a score=..." alike
+        auto at_block = [&](size_t p) { return p < size_ && mem_[p] == 'a' && (p == 0 || mem_[p - 1] == '\n'); };
         auto next_block = [&](size_t p) -> size_t {          // first block start >= p
             while (p < size_) {
                 if (at_block(p)) return p;
@@ -308,7 +310,7 @@ private:
                             if (b.strand != '+' && concatenate_) die("Reference sequence is not on the + strand (%s at position %ld)!", who.c_str(), (long)b.start0);
                         }
                         c.blocks.push_back(bi);
-                    } else if (!first_block || true) {
+                    } else {
                         // a block without any species of the model contributes nothing
                         if (c.ref_id >= 0 || first_block) c.blocks.push_back(bi);
                     }

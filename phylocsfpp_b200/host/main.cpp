@@ -58,8 +58,7 @@ uint32_t precision_flag(const Args &a) {
     const std::string p = lower(a.str("precision", "f64"));
     if (p == "f64") return 0;
     if (p == "tc5") return PCSF_TRACKS_TC5;
-    if (p == "f32") return PCSF_TRACKS_FP32;
-    die("--precision must be f64, tc5 or f32");
+    die("--precision must be f64 or tc5");
 }
 
 int64_t mod3(int64_t x) { x %= 3; return x < 0 ? x + 3 : x; }
@@ -644,7 +643,7 @@ int main(int argc, char **argv) {
         printf("phylocsf_b200 — B200-native PhyloCSF++ likelihood core behind the reference's command line\n\n"
                "  phylocsf_b200 build-tracks [--output-raw-phylo BOOL] [--output-phylo BOOL] [--output-regions BOOL] [--genome-length INT]\n"
                "                             [--coding-exons FILE] [--power-threshold FLOAT] [--threads INT] [--gpus INT]\n"
-               "                             [--precision f64|tc5|f32] [--output DIR] [--mapping FILE] [--species LIST] <model> <maf>...\n"
+               "                             [--precision f64|tc5] [--output DIR] [--mapping FILE] [--species LIST] <model> <maf>...\n"
                "  phylocsf_b200 score-msa    [--strategy MLE|FIXED|OMEGA|FIXED_MEAN] [--comp-phylo BOOL] [--comp-anc BOOL] [--threads INT] [--gpus INT]\n"
                "                             [--output DIR] [--mapping FILE] [--species LIST] <model> <maf>...\n");
         return argc < 2 ? 1 : 0;

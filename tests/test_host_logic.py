@@ -10,6 +10,8 @@ from phylocsfpp_b200.maf import MafReader
 from phylocsfpp_b200.models import builtin_models, load_model
 from tests.util import random_alignment
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 
 def test_builtin_models_load():
     names = builtin_models()
@@ -154,3 +156,29 @@ def test_synthetic_workload_has_the_baseline_shape():
     assert 0.25 <= other_missing <= 0.36, other_missing
     c = synth_alignment(m, L, seed=6, device="cpu")[:, :L].numpy()
     assert (a != c).mean() > 0.3
+
+
+@pytest.fixture(scope="module")
+def tc5_check_exe(tmp_path_factory):
+    import subprocess
+    exe = os.path.join(str(tmp_path_factory.mktemp("tc5chk")), "tc5_program_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tools", "tc5_program_check.cpp")], check=True)
+    return exe
+
+
+@pytest.mark.parametrize("model,species", [("58mammals", ""), ("100vertebrates", ""), ("53birds", ""), ("7yeast", ""),
+                                           ("29mammals", "Human,Chimp,Mouse"), ("29mammals", "Human,Mouse"),
+                                           ("29mammals", "Human,Chimp,Mouse,Dog,Cow,Horse,Elephant,Armadillo,Rat,Rabbit,Cat,Megabat")])
+def test_tcgen05_step_program_on_the_cpu(tc5_check_exe, model, species):
+    """The step program of k_prune_tc5 (chain starts, GEMM steps, leaf sources in ring order, cherry tables in table order,
+    pushes / pops) interpreted on the host in FP64 equals the plain post-order Felsenstein recursion (fixed_lik.hpp:125-164) on
+    random codon columns; the FP32-class emulation of the same program stays far inside the 1e-3 deciban contract."""
+    import re
+    import subprocess
+    exe = tc5_check_exe
+    env = dict(os.environ, PHYLOCSF_B200_DATA=os.path.join(ROOT, "phylocsfpp_b200", "data"))
+    r = subprocess.run([exe, model, species, "60"], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    d64 = float(re.search(r"max \|d log z\| = (\S+)", r.stdout).group(1))
+    d32 = float(re.search(r"max \|d\| = (\S+) decibans", r.stdout).group(1))
+    assert d64 < 1e-11 and d32 < 2e-4, r.stdout

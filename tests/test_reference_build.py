@@ -235,25 +235,6 @@ def test_cli_score_msa_fixed_mean_vs_reference_msa29(golden_dir, tmp_path):
     assert r.returncode != 0 and "FIXED_MEAN" in r.stdout
 
 
-@pytest.mark.gpu
-def test_tc5_half_variant_matches(golden_dir, tmp_path):
-    """The experimental 16-epilogue-warp tcgen05 kernel (PCSF_TC5_VARIANT=half) gives the same tracks as the default one to the
-    printed digit (two threads per window only change the order of the final 64-term sum)."""
-    R = os.path.join(golden_dir, "ref-generated")
-    maf = _gunzip(os.path.join(R, "tracks12.maf.gz"), os.path.join(str(tmp_path), "tracks12.maf"))
-    outs = []
-    for variant in ("base", "half"):
-        out = os.path.join(str(tmp_path), "o_" + variant)
-        subprocess.run([BIN, "build-tracks", "--threads", "2", "--precision", "tc5", "--output", out, "12flies", maf], check=True, capture_output=True,
-                       env=dict(os.environ, PCSF_TC5_VARIANT=variant))
-        outs.append(out)
-    for n in WIGS:
-        a = open(os.path.join(outs[0], n)).read().split("\n")
-        b = open(os.path.join(outs[1], n)).read().split("\n")
-        assert len(a) == len(b)
-        assert sum(x != y for x, y in zip(a, b)) <= len(a) // 1000 + 1
-
-
 # ------------------------------------------------------------------------------------------------ 4. differential runs
 def _oracle_build_tracks(model_name, maf, threshold=0.1, species=""):
     """The oracle + reader-mirror pipeline of build-tracks: dict file name -> list of lines."""

@@ -79,3 +79,29 @@ def write_synthetic_exons(path: str, n: int = 46000, seed: int = 99) -> None:
             end = start + length
             pos[key] = end
             fh.write("%s\t%s\t%d\t%d\t%d\n" % (chrom, strand, phase, start, end))
+
+
+def prune_longdouble(tree, P: np.ndarray, pi: np.ndarray, codons: np.ndarray) -> np.ndarray:
+    """log z per window by Felsenstein pruning (fixed_lik.hpp:125-164) in x87 extended precision: 15 exponent bits, so the
+    unscaled products of 100 certain leaves (~1e-400) neither underflow nor go denormal as the reference's doubles do.
+    tree: flattened tree (child1, child2, nl, n); P [(n-1), 64, 64] row-major P_b[a][c]; codons uint8 [nl, W] (64 = gap/N)."""
+    LD = np.longdouble
+    nl, n = tree.nl, tree.n
+    W = codons.shape[1]
+    Pl = P.astype(LD)
+    alpha = [None] * n
+    msg = [None] * n
+    for v in range(n):
+        if v < nl:
+            x = codons[v].astype(np.int64)
+            col = np.ones((W, 64), LD)
+            certain = x < 64
+            col[certain] = Pl[v][:, x[certain]].T          # message of a leaf with codon x: P_v[:, x]; all ones for a gap
+            msg[v] = col
+        else:
+            a = msg[tree.child1[v]] * msg[tree.child2[v]]
+            alpha[v] = a
+            if v < n - 1:
+                msg[v] = a @ Pl[v].T                        # msg[w][a] = sum_b P_v[a][b] alpha[w][b]
+    z = alpha[n - 1] @ pi.astype(LD)
+    return np.log(z)

@@ -344,6 +344,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "WAIT_DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// The same wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or the hint expires) instead of
+// spinning through the issue slots of its scheduler — for producer warps that share a scheduler with latency-critical warps.
+__device__ __forceinline__ void mbar_wait_sleepy(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP_S:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra WAIT_DONE_S;\n"
+        "bra WAIT_LOOP_S;\n"
+        "WAIT_DONE_S:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+}
 __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");

@@ -52,12 +52,20 @@ struct EcmHost {
     std::vector<double> pstream;  // n_gemm tiles of 4096 doubles, DMMA fragment order, program order
     std::vector<double> leafPT;   // nl x 65 x 64: leafPT[l][x][a] = P_l[a][x], x = 64 -> row sums
     // tcgen05 path: one 32 KB tile per inner NON-CHERRY edge in step order (UMMA K-major no-swizzle B layout, N = 128 =
-    // [hi | lo]), one 17 KB shared-memory gather table per DIRECT leaf (a leaf whose sibling is not a leaf) in program order
-    // (64 rows x 68 floats), and, per cherry in program order, what k_build_cherry needs to tabulate the message of the edge
-    // above it: the cherry node's own P (row-major FP64) — the two leaves' columns come from leafPT
+    // [hi | lo]) and, per cherry in program order, the cherry node's own P (row-major FP64) from which k_build_rows tabulates
+    // the message of the edge above it (the leaves' columns come from leafPT)
     std::vector<float> pstream_tc5;
-    std::vector<float> leaf_tc5;
     std::vector<double> cherry_P;   // n_cherry x 64 x 64
+};
+
+// One row source of the tcgen05 program, in the order the program consumes them: the message table of a direct leaf (65 rows:
+// codon x -> P_l[:, x], row 64 = all ones) or of a cherry (65 x 65 rows: x * 65 + y), rows of 64 floats at row_base of the
+// ECM's row table.
+struct Tc5Src {
+    uint32_t row_base;
+    uint8_t l1, l2;      // leaf ids whose codons select the row; l2 = 0xff for a leaf source
+    uint8_t cherry;      // cherry number (index into cherry_P) for a cherry source
+    uint8_t pad;
 };
 
 struct ModelHost {
@@ -75,6 +83,8 @@ struct ModelHost {
     std::vector<int> tc5_leaf_order;   // direct leaves in the order the program gathers them (the leaf-table ring)
     std::vector<int> tc5_cherries;     // cherry node ids in the order the program consumes their tables
     std::vector<uint16_t> tc5_cherry_leaves;   // left leaf | right leaf << 8 of cherry k
+    std::vector<Tc5Src> tc5_srcs;      // every source, in consumption order
+    uint32_t tc5_rows = 0;             // rows of one ECM's row table
     uint32_t tc5_start = 0;            // src1 | src2 << 8 of the chain start the program begins with
     int tc5_max_stack = 0;             // pushes alive at once (depth of the global-memory stack)
     std::vector<BlsNode> bls_prog;
@@ -235,9 +245,6 @@ inline float tf32_rna(float x) {
 //   T5_POP_MUL     alpha_parent = msg * pop
 enum : uint32_t { T5_NONE = 0, T5_MUL = 1, T5_PUSH_START = 2, T5_POP_MUL = 3, T5_END = 1u << 20, T5_SRC_CHERRY = 0x80u };
 constexpr int T5_CHERRY_ROWS = 65 * 65;
-constexpr int T5_LEAF_ROW = 68;                      // floats per gather-table row: 272 B stride spreads the rows over the banks
-constexpr int T5_LEAF_FLOATS = 64 * T5_LEAF_ROW;     // 17408 B per leaf
-
 // One inner edge as the B operand of tcgen05.mma kind::tf32 (K-major, no swizzle): B[n][k], n = 0..127, k = 0..63 with
 // B[n][k] = hi(P[n][k]) for n < 64 and lo(P[n-64][k]) for n >= 64, so that D[w][0:64] + D[w][64:128] = sum_k A[w][k] P[.][k].
 // Chunk j (k = 8j..8j+7) is 4 KB contiguous; inside a chunk 8-row x 16-byte core matrices: 8-row group stride 256 B
@@ -251,15 +258,6 @@ inline void to_tc5_tile(const double *P, float *tile /* 8192 floats */) {
             tile[(k / 8) * 1024 + (n / 8) * 64 + ((k % 8) / 4) * 32 + (n % 8) * 4 + (k % 4)] = v;
         }
 }
-// Leaf gather table: row x (a certain codon) = P_l[:, x] in FP32.  A gap/N codon (id 64) is the all-ones message on
-// this path: the row sums of P_l are 1 to FP32 precision (instance.hpp:625-639 normalises the rows).
-inline void to_tc5_leaf(const double *P, float *tab /* T5_LEAF_FLOATS */) {
-    for (int x = 0; x < NS; ++x) {
-        for (int a = 0; a < NS; ++a) tab[x * T5_LEAF_ROW + a] = (float)P[a * NS + x];
-        for (int a = NS; a < T5_LEAF_ROW; ++a) tab[x * T5_LEAF_ROW + a] = 0.f;
-    }
-}
-
 inline void to_leaf_table(const double *P, double *pt /* 65 x 64 */) {
     for (int a = 0; a < NS; ++a) {
         double rs = 0.0;
@@ -333,10 +331,21 @@ struct Tc5Emit {
         }
     }
     uint32_t src(int c) {                 // c is 'L' or 'C': registers its table in program order
-        if (kind[c] == 'L') { m.tc5_leaf_order.push_back(c); return (uint32_t)c; }
+        Tc5Src d{};
+        d.row_base = m.tc5_rows;
+        if (kind[c] == 'L') {
+            m.tc5_leaf_order.push_back(c);
+            d.l1 = (uint8_t)c; d.l2 = 0xff;
+            m.tc5_rows += 65;
+            m.tc5_srcs.push_back(d);
+            return (uint32_t)c;
+        }
         const uint32_t k = (uint32_t)m.tc5_cherries.size();
         m.tc5_cherries.push_back(c);
         m.tc5_cherry_leaves.push_back((uint16_t)(m.child1[c] | (m.child2[c] << 8)));
+        d.l1 = (uint8_t)m.child1[c]; d.l2 = (uint8_t)m.child2[c]; d.cherry = (uint8_t)k;
+        m.tc5_rows += T5_CHERRY_ROWS;
+        m.tc5_srcs.push_back(d);
         return T5_SRC_CHERRY | k;
     }
     void alpha(int i) {                   // leaves alpha_i as the running partial
@@ -365,7 +374,7 @@ struct Tc5Emit {
 // Returns nullptr on success.
 inline const char *prepare_tc5_program(ModelHost &m) {
     m.tc5_steps.clear(); m.tc5_edges.clear(); m.tc5_leaf_order.clear(); m.tc5_cherries.clear(); m.tc5_cherry_leaves.clear();
-    m.tc5_max_stack = 0; m.tc5_start = 0;
+    m.tc5_max_stack = 0; m.tc5_start = 0; m.tc5_srcs.clear(); m.tc5_rows = 0;
     Tc5Emit e(m);
     e.classify(m.n - 1);
     e.alpha(m.n - 1);
@@ -499,9 +508,6 @@ inline std::string prepare_model(ModelHost &m, int nl, const int16_t *c1, const 
         e.pstream_tc5.resize(m.tc5_edges.size() * (size_t)8192);
         for (size_t st = 0; st < m.tc5_edges.size(); ++st)
             to_tc5_tile(e.P.data() + (size_t)m.tc5_edges[st] * NS * NS, e.pstream_tc5.data() + st * 8192);
-        e.leaf_tc5.resize(m.tc5_leaf_order.size() * (size_t)T5_LEAF_FLOATS);
-        for (size_t k = 0; k < m.tc5_leaf_order.size(); ++k)
-            to_tc5_leaf(e.P.data() + (size_t)m.tc5_leaf_order[k] * NS * NS, e.leaf_tc5.data() + k * T5_LEAF_FLOATS);
         e.cherry_P.resize(m.tc5_cherries.size() * (size_t)NS * NS);
         for (size_t k = 0; k < m.tc5_cherries.size(); ++k)
             std::memcpy(e.cherry_P.data() + k * NS * NS, e.P.data() + (size_t)m.tc5_cherries[k] * NS * NS, sizeof(double) * NS * NS);

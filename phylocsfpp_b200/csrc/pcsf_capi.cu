@@ -71,13 +71,14 @@ struct pcsf_model {
     double *d_pstream[2] = {nullptr, nullptr}, *d_leafPT[2] = {nullptr, nullptr};
     double *d_pi[2] = {nullptr, nullptr}, *d_logpi[2] = {nullptr, nullptr};
     double *d_eig[2] = {nullptr, nullptr};   // lambda[64] | SR[4096] | SRinv[4096]
-    float *d_pstream_tc5[2] = {nullptr, nullptr}, *d_leaf_tc5[2] = {nullptr, nullptr};
-    float *d_cherry_tc5[2] = {nullptr, nullptr};   // [n_cherry][65*65][64] message tables of the edges above cherries (k_build_cherry)
-    uint16_t *d_cherry_leaves = nullptr;
+    float *d_pstream_tc5[2] = {nullptr, nullptr};
+    float *d_rowtab_tc5[2] = {nullptr, nullptr};   // [tc5_rows][64] leaf and cherry message tables in program order (k_build_rows)
+    Tc5Src *d_tc5_srcs = nullptr;
     uint32_t *d_tc5_steps = nullptr;
     float *d_tc5_scratch = nullptr;      // stack spill of k_prune_tc5: [sm_count][2][max_stack][T5_STACK_ENTRY_FLOATS]
     size_t prune_tc5_smem = 0;
-    int tc5_nstage = 2, tc5_nlstage = 3;
+    int tc5_nstage = 2, tc5_nids = 1;
+    DevBuf tc5_ids;                      // codon ids of the unique windows, [pairs][2][nl][128] (k_tc5_ids)
     int32_t *d_program = nullptr;
     BlsInner *d_bls_prog = nullptr;
     float *d_bl = nullptr;
@@ -148,7 +149,6 @@ extern "C" pcsf_status pcsf_model_create(const pcsf_model_desc *d, int device, p
         if ((st = upload(e.pstream.data(), e.pstream.size() * 8, (void **)&m->d_pstream[w]))) return st;
         if ((st = upload(e.leafPT.data(), e.leafPT.size() * 8, (void **)&m->d_leafPT[w]))) return st;
         if ((st = upload(e.pstream_tc5.data(), e.pstream_tc5.size() * 4, (void **)&m->d_pstream_tc5[w]))) return st;
-        if ((st = upload(e.leaf_tc5.data(), e.leaf_tc5.size() * 4, (void **)&m->d_leaf_tc5[w]))) return st;
         if ((st = upload(e.pi, 64 * 8, (void **)&m->d_pi[w]))) return st;
         if ((st = upload(e.logpi, 64 * 8, (void **)&m->d_logpi[w]))) return st;
         std::vector<double> eig(64 + 2 * 4096);
@@ -161,15 +161,15 @@ extern "C" pcsf_status pcsf_model_create(const pcsf_model_desc *d, int device, p
     if ((st = upload(m->host.tc5_steps.data(), m->host.tc5_steps.size() * 4, (void **)&m->d_tc5_steps))) return st;
     CK(cudaMalloc(&m->d_tc5_scratch, (size_t)m->sm_count * 2 * std::max(1, m->host.tc5_max_stack) * T5_STACK_ENTRY_FLOATS * 4));
     {
-        // cherry message tables: FP64 on the device from the cherry nodes' P and the two leaves' columns, stored as FP32 rows
-        const int nc = (int)m->host.tc5_cherries.size();
-        if ((st = upload(m->host.tc5_cherry_leaves.data(), (size_t)nc * 2, (void **)&m->d_cherry_leaves))) return st;
-        for (int w = 0; w < 2 && nc > 0; ++w) {
+        // row tables (leaf columns and cherry messages): FP64 on the device from the leaves' columns and the cherry nodes' P, FP32 rows
+        const int ns = (int)m->host.tc5_srcs.size();
+        if ((st = upload(m->host.tc5_srcs.data(), (size_t)ns * sizeof(Tc5Src), (void **)&m->d_tc5_srcs))) return st;
+        for (int w = 0; w < 2; ++w) {
             double *d_cp = nullptr;
             if ((st = upload(m->host.ecm[w].cherry_P.data(), m->host.ecm[w].cherry_P.size() * 8, (void **)&d_cp))) return st;
-            cudaError_t e = cudaMalloc(&m->d_cherry_tc5[w], (size_t)nc * T5_CHERRY_ROWS * 64 * 4);
+            cudaError_t e = cudaMalloc(&m->d_rowtab_tc5[w], (size_t)m->host.tc5_rows * 64 * 4);
             if (e == cudaSuccess) {
-                k_build_cherry<<<dim3(65, nc), 64>>>(d_cp, m->d_leafPT[w], m->d_cherry_leaves, m->d_cherry_tc5[w]);
+                k_build_rows<<<dim3(65, ns), 64>>>(m->d_tc5_srcs, d_cp, m->d_leafPT[w], m->d_rowtab_tc5[w]);
                 e = cudaGetLastError();
                 if (e == cudaSuccess) e = cudaDeviceSynchronize();
             }
@@ -177,10 +177,10 @@ extern "C" pcsf_status pcsf_model_create(const pcsf_model_desc *d, int device, p
             CK(e);
         }
     }
-    prune_tc5_pick_stages(m->host.nl, (int)m->host.tc5_steps.size(), (int)m->host.tc5_cherries.size(), &m->tc5_nstage, &m->tc5_nlstage);
+    prune_tc5_pick_stages(m->host.nl, (int)m->host.tc5_steps.size(), (int)m->host.tc5_srcs.size(), &m->tc5_nstage, &m->tc5_nids);
     if (const char *e = getenv("PCSF_TC5_NSTAGE")) m->tc5_nstage = std::max(2, std::min(m->tc5_nstage, atoi(e)));
-    if (const char *e = getenv("PCSF_TC5_NLSTAGE")) m->tc5_nlstage = std::max(3, std::min(m->tc5_nlstage, atoi(e)));
-    m->prune_tc5_smem = prune_tc5_smem_bytes(m->host.nl, (int)m->host.tc5_steps.size(), (int)m->host.tc5_cherries.size(), m->tc5_nstage, m->tc5_nlstage);
+    if (const char *e = getenv("PCSF_TC5_NIDS")) m->tc5_nids = std::max(1, std::min(m->tc5_nids, atoi(e)));
+    m->prune_tc5_smem = prune_tc5_smem_bytes(m->host.nl, (int)m->host.tc5_steps.size(), (int)m->host.tc5_srcs.size(), m->tc5_nstage, m->tc5_nids);
     CK(cudaFuncSetAttribute(k_prune_tc5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->prune_tc5_smem));
     if ((st = upload(m->host.bls_inner.data(), m->host.bls_inner.size() * sizeof(BlsInner), (void **)&m->d_bls_prog))) return st;
     if ((st = upload(m->host.bl.data(), m->host.bl.size() * 4, (void **)&m->d_bl))) return st;
@@ -221,18 +221,18 @@ extern "C" void pcsf_model_destroy(pcsf_model *m) {
     if (!m) return;
     cudaSetDevice(m->device);
     for (int w = 0; w < 2; ++w) {
-        cudaFree(m->d_pstream[w]); cudaFree(m->d_leafPT[w]); cudaFree(m->d_cherry_tc5[w]); cudaFree(m->d_pstream_tc5[w]); cudaFree(m->d_leaf_tc5[w]); cudaFree(m->d_pi[w]); cudaFree(m->d_logpi[w]);
+        cudaFree(m->d_pstream[w]); cudaFree(m->d_leafPT[w]); cudaFree(m->d_rowtab_tc5[w]); cudaFree(m->d_pstream_tc5[w]); cudaFree(m->d_pi[w]); cudaFree(m->d_logpi[w]);
         cudaFree(m->d_eig[w]);
     }
     cudaFree(m->d_program); cudaFree(m->d_bls_prog); cudaFree(m->d_bl); cudaFree(m->d_gemm_edges);
-    cudaFree(m->d_bad); cudaFree(m->d_nuniq); cudaFree(m->d_tc5_steps); cudaFree(m->d_tc5_scratch); cudaFree(m->d_cherry_leaves);
+    cudaFree(m->d_bad); cudaFree(m->d_nuniq); cudaFree(m->d_tc5_steps); cudaFree(m->d_tc5_scratch); cudaFree(m->d_tc5_srcs);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     if (m->h2d_stream) cudaStreamDestroy(m->h2d_stream);
     for (cudaEvent_t e : m->ev_h2d) cudaEventDestroy(e);
     if (m->ev_chunk) cudaEventDestroy(m->ev_chunk);
     DevBuf *bufs[] = {&m->codes, &m->klo, &m->khi, &m->slot, &m->flag, &m->uniq, &m->pidx, &m->table, &m->slotmin,
-                      &m->bsums, &m->logz, &m->anc, &m->misc, &m->io_in, &m->io_out, &m->perwin, &m->mle};
+                      &m->bsums, &m->logz, &m->anc, &m->misc, &m->io_in, &m->io_out, &m->perwin, &m->mle, &m->tc5_ids};
     for (DevBuf *b : bufs) b->release();
     for (auto &e : m->ev) if (e) cudaEventDestroy(e);
     delete m;
@@ -321,28 +321,30 @@ static pcsf_status dedup_and_prune(pcsf_model *m, const WinSpace &ws, uint32_t n
     }
     if (m->timing) CK(cudaEventRecord(m->ev[2], st));
     if (prec == 2) {
+        // codon ids of the unique windows in the producers' layout, one 2 x nl x 128-byte block per pair of tiles
+        const uint32_t mp = (nwin + 255) / 256;
+        CK(m->tc5_ids.reserve((size_t)mp * 2 * m->host.nl * 128));
+        m->launches++;
+        k_tc5_ids<<<std::min<uint32_t>(mp, (uint32_t)m->sm_count * 8), 256, 0, st>>>(ws, m->uniq.as<uint32_t>(), d_nuniq_slot, m->tc5_ids.as<uint8_t>());
+        CK(cudaGetLastError());
         PruneTc5Args ta{};
-        ta.ws = ws;
-        ta.uniq = m->uniq.as<uint32_t>();
+        ta.ids = m->tc5_ids.as<uint8_t>();
+        ta.nl = m->host.nl;
+        ta.nids = m->tc5_nids;
         ta.n_unique = d_nuniq_slot;
         ta.steps = m->d_tc5_steps;
         ta.n_steps = (int)m->host.tc5_steps.size();
         ta.max_stack = m->host.tc5_max_stack;
-        ta.start = m->host.tc5_start;
-        ta.n_leaf_tabs = (int)m->host.tc5_leaf_order.size();
-        ta.n_cherry = (int)m->host.tc5_cherries.size();
-        ta.cherry_leaves = m->d_cherry_leaves;
+        ta.n_src = (int)m->host.tc5_srcs.size();
+        ta.srcs = m->d_tc5_srcs;
         ta.nstage = m->tc5_nstage;
-        ta.nlstage = m->tc5_nlstage;
         ta.scratch = m->d_tc5_scratch;
         for (int w = 0; w < 2; ++w) {
             ta.pstream[w] = m->d_pstream_tc5[w];
-            ta.leaftab[w] = m->d_leaf_tc5[w];
-            ta.cherrytab[w] = m->d_cherry_tc5[w];
+            ta.rowtab[w] = m->d_rowtab_tc5[w];
             ta.pi[w] = m->d_pi[w];
             ta.logz[w] = m->logz.as<double>() + (size_t)w * nwin;
         }
-        const uint32_t mp = (nwin + 255) / 256;
         const unsigned gridt = std::min<uint32_t>((uint32_t)m->sm_count, std::max<uint32_t>(1u, mp));
         m->launches++;
         k_prune_tc5<<<gridt, T5_THREADS, m->prune_tc5_smem, st>>>(ta);

@@ -1,6 +1,7 @@
 // prune_tc5.cuh — k_prune_tc5: Felsenstein pruning on the 5th-generation tensor cores (tcgen05.mma kind::tf32,
-// accumulators and the A operand in TMEM, P tiles and leaf tables streamed by bulk TMA, cherry messages gathered from
-// L2-resident tables).  FP32-class arithmetic with per-window log-scaling; the FP64 DMMA kernel (k_prune) stays the parity anchor.
+// accumulators and the A operand in TMEM, P tiles streamed by bulk TMA, leaf and cherry messages gathered from L2-resident
+// row tables by dedicated producer warps).  FP32-class arithmetic with per-window log-scaling; the FP64 DMMA kernel (k_prune)
+// stays the parity anchor.
 //
 // Formulation (ensure_alpha, fixed_lik.hpp:125-164).  For 128 codon windows at a time every edge above a NON-CHERRY inner
 // node c is one GEMM  D[w][a] = sum_b A[w][b] * P_c[a][b]  on the tensor core (M = 128 windows, K = 64 child states):
@@ -10,24 +11,30 @@
 // reads its 4 KB A slab from TMEM at 64 B/clk, i.e. ~64 cycles whatever its N <= 128 (tools/tc5_probe.cu), so the
 // side-by-side layout is what makes two instructions per k-step enough.
 // LEAF edges are not GEMMs: the message of a leaf with codon x is column x of P_l (all ones for a gap/N codon, the row
-// sums of fixed_lik.hpp:111-118).  The epilogue threads gather it from a 17 KB per-leaf table that TMA streams into shared
-// memory in program order — and they do so WHILE their GEMM runs, so leaves cost no tensor time and no latency.
+// sums of fixed_lik.hpp:111-118): one row of a 65-row table.
 // CHERRY edges are not GEMMs either (round 2): the message of the edge above a node whose two children are leaves depends only on
-// the two codons, P_c . (P_l[:, x] * P_r[:, y]), 65 x 65 rows of 64 floats tabulated once per model in FP64 (k_build_cherry) and
-// kept in global memory (1.08 MB per cherry and ECM: L2 resident).  Every epilogue warp copies the 32 rows of its own windows
-// with 16-byte cp.async (sixteen lanes per 256-byte row: full sectors) into a private, XOR-swizzled 8 KB staging area one
-// cherry ahead of the program, and each thread then reads its own row without bank conflicts.  That removes 17 of 56 GEMMs,
-// 34 of 58 leaf gathers and half of the stack pushes for 58mammals (28 of 98, 56 of 100 for 100vertebrates).
+// the two codons, P_c . (P_l[:, x] * P_r[:, y]): 65 x 65 rows of 64 floats tabulated once per model in FP64 (k_build_rows).  That
+// removes 17 of 56 GEMMs, 34 of 58 leaf factors and half of the stack pushes for 58mammals (28 of 98, 56 of 100 for 100vertebrates).
+// Both kinds are ROW SOURCES of one row table per ECM in global memory (19 MB for 58mammals: L2 resident), consumed in program
+// order.  Six PRODUCER warps copy the rows of the 128 windows of a chain with 16-byte cp.async (sixteen lanes per 256-byte row: full
+// sectors; jobs of 32 rows dealt round-robin) into one of the chain's two XOR-swizzled 32 KB staging buffers, two sources ahead
+// of the program, and signal a full mbarrier (cp.async.mbarrier.arrive); every epilogue thread then reads its own row with
+// conflict-free LDS.128 and releases the buffer through an empty mbarrier.  The epilogue warps — the critical path of the
+// kernel — neither compute a row index nor issue a copy.  (Round 1 streamed whole leaf tables through a shared-memory ring and
+// gathered from them with 2.6-way bank conflicts, 1000-2000 cycles per gather; letting the epilogue warps issue the cp.async
+// themselves cost ~1000 cycles per step on the critical path.)
+// The codon ids the row indices are computed from come from k_tc5_ids: one pass that writes, per pair of 128-window tiles, the
+// [chain][leaf][window] byte block the producers want in shared memory, so that a single bulk TMA copy brings it in (the
+// epilogue threads used to gather 3 bytes per leaf and window from the code matrix: 18 k cycles per pair with the tensor pipe idle).
 //
-// One persistent CTA per SM works on a PAIR of 128-window tiles (chains X and Y) that share both TMA rings: while the
+// One persistent CTA per SM works on a PAIR of 128-window tiles (chains X and Y) that share the tile ring: while the
 // tensor core runs chain Y's GEMM of step g, chain X's epilogue turns D_g into A_{g+1} (and vice versa).
 //   warps 0-3   epilogue of chain X: thread = window = TMEM lane; the 64-state partial lives in registers
 //   warps 4-7   epilogue of chain Y        TMEM columns 256c..256c+255: two 128-column regions, A_g in one, D_g in the
 //   warp  8     MMA issue (one elected lane)    other; A_{g+1} overwrites D_g in place
 //   warp  9     TMA producer, inner-edge tiles (32 KB each, 2- or 3-stage full/empty mbarrier ring)
-//   warp 10     TMA producer, leaf tables (17 KB each, up to 6 stages: both chains read every table, so a stage lives
-//               until the trailing chain has used it)
-// The producer warpgroup gives its registers to the epilogue warpgroups (setmaxnreg 40 / 232).
+//   warps 10-15 row producers (warp 10 also issues the bulk copy of the next pair's codon ids)
+// The producer warpgroups give their registers to the epilogue warpgroups (setmaxnreg 40 / 216).
 // Waiting sibling partials (stack depth = Strahler number over the non-cherry inner nodes - 1) spill to an L2-resident scratch
 // in global memory, every thread only ever touching its own column: the push is issued after the next A has been handed to
 // the tensor core, the pop is prefetched while the GEMM runs, so neither is on the critical path.
@@ -40,64 +47,96 @@ namespace pcsf {
 
 constexpr int T5_MAX_NSTAGE = 3;         // inner-edge tile ring (stages chosen at model creation: what fits)
 constexpr int T5_TILE_BYTES = 32768;
-constexpr int T5_MAX_NLSTAGE = 6;        // leaf table ring
-constexpr int T5_LEAF_BYTES = T5_LEAF_FLOATS * 4;
-constexpr int T5_THREADS = 384;
+constexpr int T5_THREADS = 512;
+constexpr int T5_NPROD = 6;              // row producer warps (10..15)
 constexpr int T5_STACK_ENTRY_FLOATS = 64 * 128 + 128;   // 128 windows x 64 states + 128 exponents
+constexpr int T5_ROW_STAGE_BYTES = 128 * 256;           // one staging buffer of one chain: the rows of its 128 windows
 
 struct PruneTc5Args {
-    WinSpace ws;
-    const uint32_t *uniq;
     const uint32_t *n_unique;
     const uint32_t *steps;
-    int n_steps, max_stack;
-    uint32_t start;              // src1 | src2 << 8: the chain start the program begins with
-    int n_leaf_tabs, n_cherry;
-    int nstage, nlstage;         // ring depths
+    int nl, n_steps, max_stack;
+    int n_src;                   // row sources per ECM pass, in consumption order
+    int nstage;                  // tile ring depth
+    int nids;                    // codon-id ring depth (2 when it fits, else 1)
+    const uint8_t *ids;          // [pairs][2 chains][nl][128] codon ids (k_tc5_ids)
     const float *pstream[2];     // [n_steps][8192]
-    const float *leaftab[2];     // [n_leaf_tabs][T5_LEAF_FLOATS], program order
-    const float *cherrytab[2];   // [n_cherry][T5_CHERRY_ROWS][64], program order
-    const uint16_t *cherry_leaves;   // [n_cherry] left leaf | right leaf << 8
+    const float *rowtab[2];      // [rows][64]: leaf and cherry message tables (Tc5Src::row_base)
+    const Tc5Src *srcs;          // [n_src]
     const double *pi[2];
     double *logz[2];
     float *scratch;              // [grid][2][max_stack][T5_STACK_ENTRY_FLOATS]
 };
 
-constexpr int T5_CHERRY_STAGE_BYTES = 32 * 256;     // per epilogue warp: the rows of its 32 windows
-
-__host__ __device__ inline size_t prune_tc5_smem_bytes(int nl, int n_steps, int n_cherry, int nstage, int nlstage) {
-    size_t b = (size_t)nstage * T5_TILE_BYTES + (size_t)nlstage * T5_LEAF_BYTES;
-    b += (size_t)8 * T5_CHERRY_STAGE_BYTES;                 // cherry row staging
-    b += (size_t)2 * nl * 128;                              // leaf codon ids of both tiles
+__host__ __device__ inline size_t prune_tc5_smem_bytes(int nl, int n_steps, int n_src, int nstage, int nids) {
+    size_t b = (size_t)nstage * T5_TILE_BYTES;
+    b += (size_t)2 * 2 * T5_ROW_STAGE_BYTES;                // row staging: 2 chains x 2 buffers
+    b += (size_t)T5_NPROD * 128;                            // row index exchange, 32 x 4 bytes per producer warp
+    b += (size_t)nids * 2 * nl * 128;                       // codon ids of both tiles
     b += (size_t)(((n_steps + 1) * 4 + 15) / 16) * 16;      // steps
-    b += (size_t)(((n_cherry + 1) * 2 + 15) / 16) * 16;     // cherry leaves
+    b += (size_t)(n_src + 1) * sizeof(Tc5Src);              // sources
     b += 2 * 64 * 8;                                        // pi
-    b += 32 * 8;                                            // mbarriers + TMEM base (2*3 + 2*6 + 4 + 2 barriers)
+    b += 32 * 8;                                            // mbarriers + TMEM base
     return b;
 }
-// Deepest rings that fit into one SM's shared memory.
-inline void prune_tc5_pick_stages(int nl, int n_steps, int n_cherry, int *nstage, int *nlstage) {
-    *nstage = T5_MAX_NSTAGE; *nlstage = T5_MAX_NLSTAGE;
-    while (prune_tc5_smem_bytes(nl, n_steps, n_cherry, *nstage, *nlstage) > 227 * 1024 && *nlstage > 4) --*nlstage;
-    while (prune_tc5_smem_bytes(nl, n_steps, n_cherry, *nstage, *nlstage) > 227 * 1024 && *nstage > 2) --*nstage;
-    while (prune_tc5_smem_bytes(nl, n_steps, n_cherry, *nstage, *nlstage) > 227 * 1024 && *nlstage > 3) --*nlstage;
+// Deepest rings that fit into one SM's shared memory: the codon ids double-buffered first (a single buffer exposes the bulk
+// copy's latency once per pair), then a third tile stage.
+inline void prune_tc5_pick_stages(int nl, int n_steps, int n_src, int *nstage, int *nids) {
+    *nstage = 2; *nids = 1;
+    if (prune_tc5_smem_bytes(nl, n_steps, n_src, 2, 2) <= 227 * 1024) *nids = 2;
+    if (prune_tc5_smem_bytes(nl, n_steps, n_src, 3, *nids) <= 227 * 1024) *nstage = 3;
 }
 
-// Cherry tables: T[k][x * 65 + y][a] = sum_b P_c[a][b] * u_x[b] * v_y[b] with u_x = P_l[:, x], v_y = P_r[:, y] (all ones for
-// index 64, the gap/N codon — the leaf rule of this path), FP64 accumulation, FP32 storage.  grid (65, n_cherry), 64 threads.
-__global__ void __launch_bounds__(64) k_build_cherry(const double *__restrict__ cherry_P, const double *__restrict__ leafPT,
-                                                     const uint16_t *__restrict__ cherry_leaves, float *__restrict__ tab) {
+// Codon ids of the unique windows in the layout the producers of k_prune_tc5 read: block (pair, chain) = [leaf][128 windows].
+// Windows past n_unique repeat the last one (their results are never stored).
+__global__ void __launch_bounds__(256) k_tc5_ids(const WinSpace ws, const uint32_t *__restrict__ uniq, const uint32_t *__restrict__ n_unique_p,
+                                                 uint8_t *__restrict__ ids) {
+    const uint32_t n_unique = *n_unique_p;
+    const uint32_t npairs = (n_unique + 255) / 256;
+    for (uint32_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+        const uint32_t u = pair * 256 + threadIdx.x;
+        const uint32_t lw = uniq[u < n_unique ? u : n_unique - 1];
+        int64_t o; uint32_t strand;
+        if (ws.mode == 0) { o = ws.c0 + (lw >> 1); strand = lw & 1; }
+        else { o = ws.win_off[lw]; strand = 0; }
+        const uint8_t *p = ws.codes + o;
+        uint8_t *out = ids + (size_t)pair * 2 * ws.nl * 128 + (size_t)(threadIdx.x >> 7) * ws.nl * 128 + (threadIdx.x & 127);
+        for (int s0 = 0; s0 < ws.nl; s0 += 16) {
+            uint32_t v[16][3];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const uint8_t *q = p + (int64_t)(s0 + k < ws.nl ? s0 + k : s0) * ws.ld;
+                v[k][0] = __ldg(q); v[k][1] = __ldg(q + 1); v[k][2] = __ldg(q + 2);
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+                if (s0 + k < ws.nl)
+                    out[(size_t)(s0 + k) * 128] = (uint8_t)(strand ? codon_minus(v[k][0], v[k][1], v[k][2]) : codon_plus(v[k][0], v[k][1], v[k][2]));
+        }
+    }
+}
+
+// Row table of one ECM.  grid (65, n_src), 64 threads (thread = parent state a).
+//   leaf source    row x = P_l[:, x] for x < 64, all ones for x = 64 (the gap/N codon)                    [block x writes row x]
+//   cherry source  row x * 65 + y = sum_b P_c[a][b] * u_x[b] * v_y[b], u_x = the left leaf's row x, v_y the right leaf's row y,
+//                  FP64 accumulation, FP32 storage                                                          [block x writes 65 rows]
+__global__ void __launch_bounds__(64) k_build_rows(const Tc5Src *__restrict__ srcs, const double *__restrict__ cherry_P,
+                                                   const double *__restrict__ leafPT, float *__restrict__ tab) {
     __shared__ double u[64];
     __shared__ double v[65][64];
-    const int k = blockIdx.y, x = blockIdx.x, a = threadIdx.x;
-    const int l = cherry_leaves[k] & 0xff, r = cherry_leaves[k] >> 8;
-    u[a] = x < 64 ? leafPT[((size_t)l * 65 + x) * 64 + a] : 1.0;
-    for (int y = 0; y < 65; ++y) v[y][a] = y < 64 ? leafPT[((size_t)r * 65 + y) * 64 + a] : 1.0;
+    const Tc5Src d = srcs[blockIdx.y];
+    const int x = blockIdx.x, a = threadIdx.x;
+    if (d.l2 == 0xff) {
+        tab[((size_t)d.row_base + x) * 64 + a] = x < 64 ? (float)leafPT[((size_t)d.l1 * 65 + x) * 64 + a] : 1.0f;
+        return;
+    }
+    u[a] = x < 64 ? leafPT[((size_t)d.l1 * 65 + x) * 64 + a] : 1.0;
+    for (int y = 0; y < 65; ++y) v[y][a] = y < 64 ? leafPT[((size_t)d.l2 * 65 + y) * 64 + a] : 1.0;
     __syncthreads();
     double pa[64];
 #pragma unroll
-    for (int b = 0; b < 64; ++b) pa[b] = cherry_P[(size_t)k * 4096 + a * 64 + b] * u[b];
-    float *out = tab + ((size_t)k * T5_CHERRY_ROWS + (size_t)x * 65) * 64 + a;
+    for (int b = 0; b < 64; ++b) pa[b] = cherry_P[(size_t)d.cherry * 4096 + a * 64 + b] * u[b];
+    float *out = tab + ((size_t)d.row_base + (size_t)x * 65) * 64 + a;
     for (int y = 0; y < 65; ++y) {
         double s = 0.0;
 #pragma unroll
@@ -110,26 +149,28 @@ __device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void *src) 
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *sp_ = smem;
-    const uint32_t T5_NSTAGE = a.nstage, T5_NLSTAGE = a.nlstage;
+    const uint32_t T5_NSTAGE = a.nstage;
     unsigned char *stage_buf = sp_; sp_ += (size_t)T5_NSTAGE * T5_TILE_BYTES;
-    unsigned char *leaf_buf = sp_; sp_ += (size_t)T5_NLSTAGE * T5_LEAF_BYTES;
-    unsigned char *cherry_buf = sp_; sp_ += (size_t)8 * T5_CHERRY_STAGE_BYTES;
-    uint8_t *ids = sp_; sp_ += (size_t)2 * a.ws.nl * 128;
+    unsigned char *row_buf = sp_; sp_ += (size_t)2 * 2 * T5_ROW_STAGE_BYTES;       // [chain][buffer][128 rows][256 B]
+    uint32_t *row_xchg = reinterpret_cast<uint32_t *>(sp_); sp_ += (size_t)T5_NPROD * 128;
+    uint8_t *ids = sp_; sp_ += (size_t)a.nids * 2 * a.nl * 128;                    // [slot][chain][leaf][128]
     uint32_t *steps = reinterpret_cast<uint32_t *>(sp_); sp_ += (size_t)(((a.n_steps + 1) * 4 + 15) / 16) * 16;
-    uint16_t *cherry_leaves = reinterpret_cast<uint16_t *>(sp_); sp_ += (size_t)(((a.n_cherry + 1) * 2 + 15) / 16) * 16;
+    Tc5Src *srcs = reinterpret_cast<Tc5Src *>(sp_); sp_ += (size_t)(a.n_src + 1) * sizeof(Tc5Src);
     double *s_pi = reinterpret_cast<double *>(sp_); sp_ += 2 * 64 * 8;
     uint64_t *full = reinterpret_cast<uint64_t *>(sp_);
     uint64_t *empty = full + T5_MAX_NSTAGE;
-    uint64_t *lfull = empty + T5_MAX_NSTAGE;
-    uint64_t *lempty = lfull + T5_MAX_NLSTAGE;
-    uint64_t *a_ready = lempty + T5_MAX_NLSTAGE;   // [2 chains][2 halves] epilogue -> MMA: states 0..31 / 32..63 of the step's A are in TMEM
-    uint64_t *d_ready = a_ready + 4;           // [2] MMA -> epilogue: D of the step is complete
-    uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(d_ready + 2);
+    uint64_t *a_ready = empty + T5_MAX_NSTAGE;     // [2 chains][2 halves] epilogue -> MMA: states 0..31 / 32..63 of the step's A are in TMEM
+    uint64_t *d_ready = a_ready + 4;               // [2] MMA -> epilogue: D of the step is complete
+    uint64_t *row_full = d_ready + 2;              // [2 chains][2 buffers] producers -> epilogue: the 128 rows of a source have landed
+    uint64_t *row_empty = row_full + 4;            // [2][2] epilogue -> producers: every thread of the chain has read its row
+    uint64_t *ids_full = row_empty + 4;            // [2 slots] bulk copy of a pair's codon ids has landed
+    uint64_t *ids_empty = ids_full + 2;            // [2] every producer warp has computed its last row index of the pair
+    uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(ids_empty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #ifdef PCSF_TC5_TRACE
@@ -140,14 +181,15 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
 #endif
     if (tid == 0) {
         for (int s = 0; s < T5_MAX_NSTAGE; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int s = 0; s < T5_MAX_NLSTAGE; ++s) { mbar_init(lfull + s, 1); mbar_init(lempty + s, 8); }
         for (int c = 0; c < 2; ++c) { for (int k = 0; k < 2; ++k) mbar_init(a_ready + 2 * c + k, 128); mbar_init(d_ready + c, 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(row_full + i, 128); mbar_init(row_empty + i, 128); }   // 4 jobs x 32 lanes / 128 readers
+        for (int i = 0; i < 2; ++i) { mbar_init(ids_full + i, 1); mbar_init(ids_empty + i, T5_NPROD); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 8) { tc5::tmem_alloc(tmem_base_slot, 512); tc5::tmem_relinquish(); }
     for (int i = tid; i < a.n_steps; i += blockDim.x) steps[i] = a.steps[i];
-    for (int i = tid; i < a.n_cherry; i += blockDim.x) cherry_leaves[i] = a.cherry_leaves[i];
-    for (int i = tid; i < 128; i += blockDim.x) s_pi[i] = a.pi[i >> 6][i & 63];
+    for (int i = tid; i < a.n_src; i += blockDim.x) srcs[i] = a.srcs[i];
+    for (int i = tid; i < 128; i += blockDim.x) s_pi[i] = (i >> 6 ? a.pi[1] : a.pi[0])[i & 63];
     tc5::fence_before_sync();
     __syncthreads();
     tc5::fence_after_sync();
@@ -155,6 +197,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
 
     const uint32_t n_unique = *a.n_unique;
     const uint32_t npairs = (n_unique + 255) / 256;
+    const int n_src2 = 2 * a.n_src;                 // sources of a pair: both ECM passes
 
     if (warp >= 8) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -168,20 +211,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
                             const uint32_t st = use % T5_NSTAGE;
                             mbar_wait(empty + st, ((use / T5_NSTAGE) & 1) ^ 1);
                             mbar_arrive_expect_tx(full + st, T5_TILE_BYTES);
-                            tma_bulk_g2s(stage_buf + (size_t)st * T5_TILE_BYTES, a.pstream[m] + (size_t)s * 8192, T5_TILE_BYTES, full + st);
-                        }
-            }
-        } else if (warp == 10) {
-            // ---- TMA producer: leaf gather tables in program order
-            if (lane == 0) {
-                uint32_t use = 0;
-                for (uint32_t pair = blockIdx.x; pair < npairs; pair += gridDim.x)
-                    for (int m = 0; m < 2; ++m)
-                        for (int k = 0; k < a.n_leaf_tabs; ++k, ++use) {
-                            const uint32_t st = use % T5_NLSTAGE;
-                            mbar_wait(lempty + st, ((use / T5_NLSTAGE) & 1) ^ 1);
-                            mbar_arrive_expect_tx(lfull + st, T5_LEAF_BYTES);
-                            tma_bulk_g2s(leaf_buf + (size_t)st * T5_LEAF_BYTES, a.leaftab[m] + (size_t)k * T5_LEAF_FLOATS, T5_LEAF_BYTES, lfull + st);
+                            tma_bulk_g2s(stage_buf + (size_t)st * T5_TILE_BYTES, (m ? a.pstream[1] : a.pstream[0]) + (size_t)s * 8192, T5_TILE_BYTES, full + st);
                         }
             }
         } else if (warp == 8) {
@@ -225,125 +255,112 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
                             T5_TRACE(2, s, 2 * c + 1);
                         }
                     }
+        } else {
+            // ---- row producers.  Job j of a pair = (source g, chain c, quarter q) with j = (g * 2 + c) * 4 + q: the rows of windows
+            // 32q..32q+31 of chain c for source g (g = ECM * n_src + k, consumed in this order) go to the chain's staging buffer g & 1.
+            // The jobs are dealt round-robin over the six warps; every warp works through its jobs in order, so the lowest
+            // unfinished job never waits for a higher one (no deadlock).  Chunk ch (16 bytes) of row rr sits at chunk position
+            // (ch & 8) | ((ch ^ rr) & 7): the sixteen lanes that copy one row write two full 128-byte lines, and the eight threads of a
+            // quarter warp that later read chunk j of their OWN rows (LDS.128) hit eight different bank groups.
+            const int pw = warp - 10;
+            uint32_t *xchg = row_xchg + pw * 32;
+            const uint32_t row_s = tc5::smem_addr(row_buf);
+            const int jobs_per_pair = n_src2 * 8;
+            const int half = lane >> 4, ch = lane & 15;
+            const size_t ids_slot_bytes = (size_t)2 * a.nl * 128;
+            uint32_t it = 0;                               // pair iteration of this CTA
+            uint32_t J = pw;                               // global job counter of this warp (over all pairs of the CTA)
+            const uint32_t my_pairs = npairs > blockIdx.x ? (npairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+            // warp 10, lane 0: bulk copy of the codon ids of pair iteration k into slot k % nids
+            auto load_ids = [&](uint32_t k) {
+                const uint32_t slot = k % a.nids, round = k / a.nids;
+                mbar_wait_sleepy(ids_empty + slot, (round & 1) ^ 1);
+                mbar_arrive_expect_tx(ids_full + slot, (uint32_t)ids_slot_bytes);
+                tma_bulk_g2s(ids + slot * ids_slot_bytes, a.ids + ((size_t)blockIdx.x + (size_t)k * gridDim.x) * ids_slot_bytes,
+                             (uint32_t)ids_slot_bytes, ids_full + slot);
+            };
+            if (pw == 0 && lane == 0)
+                for (uint32_t k = 0; k < (uint32_t)a.nids - 1 && k < my_pairs; ++k) load_ids(k);
+            for (; it < my_pairs; ++it) {
+                if (pw == 0 && lane == 0 && it + a.nids - 1 < my_pairs) load_ids(it + a.nids - 1);
+                __syncwarp();
+                const uint32_t slot = it % a.nids;
+                mbar_wait_sleepy(ids_full + slot, (it / a.nids) & 1);
+                const uint8_t *pids = ids + slot * ids_slot_bytes;
+                const uint32_t jend = (it + 1) * (uint32_t)jobs_per_pair;
+                for (; J < jend; J += T5_NPROD) {
+                    const uint32_t j = J - it * (uint32_t)jobs_per_pair;
+                    const uint32_t q = j & 3, c = (j >> 2) & 1, g = j >> 3;
+                    const uint32_t G = it * (uint32_t)n_src2 + g;                    // running source number of the chain
+                    const int m = g >= (uint32_t)a.n_src ? 1 : 0;
+                    const Tc5Src d = srcs[g - m * a.n_src];
+                    const uint8_t *wid = pids + (size_t)c * a.nl * 128 + q * 32 + lane;
+                    const uint32_t x = wid[(uint32_t)d.l1 * 128];
+                    const uint32_t myrow = d.row_base + (d.l2 == 0xff ? x : x * 65u + wid[(uint32_t)d.l2 * 128]);
+                    // every lane copies one 16-byte chunk of sixteen rows (lanes 0-15: the even windows, lanes 16-31: the odd ones): the row
+                    // indices change hands through 128 bytes of shared memory, even windows first
+                    xchg[(lane & 1) * 16 + (lane >> 1)] = myrow;
+                    __syncwarp();
+                    uint32_t rows[16];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint4 v = reinterpret_cast<const uint4 *>(xchg + half * 16)[k];
+                        rows[4 * k] = v.x; rows[4 * k + 1] = v.y; rows[4 * k + 2] = v.z; rows[4 * k + 3] = v.w;
+                    }
+                    __syncwarp();
+                    const uint32_t b = c * 2 + (G & 1);
+                    mbar_wait(row_empty + b, ((G >> 1) & 1) ^ 1);
+                    const float *tab = (m ? a.rowtab[1] : a.rowtab[0]) + ch * 4;
+                    const uint32_t dst = row_s + b * T5_ROW_STAGE_BYTES + q * 32 * 256;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int rr = 2 * i + half;                      // the window (row of the quarter) this lane copies a chunk of
+                        cp_async_16(dst + rr * 256 + (((ch & 8) | ((ch ^ rr) & 7)) << 4), tab + (size_t)rows[i] * 64);
+                    }
+                    // the lane's arrival on the full barrier is triggered when all of its copies above have landed
+                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc5::smem_addr(row_full + b)) : "memory");
+                }
+                __syncwarp();
+                if (lane == 0) { tc5::fence_proxy_async_smem(); mbar_arrive(ids_empty + slot); }   // the slot is refilled by TMA (async proxy)
+            }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
         // ---- epilogue warps: chain c, thread = window t = TMEM lane t
         const int c = warp >> 2, t = tid & 127;
         const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + c * 256;
-        uint8_t *myids = ids + (size_t)c * a.ws.nl * 128 + t;                      // [leaf * 128]
         float *stk = a.scratch + ((size_t)blockIdx.x * 2 + c) * (size_t)(a.max_stack > 0 ? a.max_stack : 1) * T5_STACK_ENTRY_FLOATS;
-        uint32_t use = 0, luse = 0;
-
-        // L (= or *=) message of the next leaf in program order, gathered from its shared-memory table
-        auto gather = [&](float (&L)[64], int leaf, bool mul) {
-            const uint32_t st = luse % T5_NLSTAGE;
-            mbar_wait(lfull + st, (luse / T5_NLSTAGE) & 1);
-            const uint32_t x = myids[leaf * 128];
-            if (x != 64u) {
-                const float4 *row = reinterpret_cast<const float4 *>(leaf_buf + (size_t)st * T5_LEAF_BYTES) + x * (T5_LEAF_ROW / 4);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float4 v = row[j];
-                    if (mul) { L[4 * j] *= v.x; L[4 * j + 1] *= v.y; L[4 * j + 2] *= v.z; L[4 * j + 3] *= v.w; }
-                    else { L[4 * j] = v.x; L[4 * j + 1] = v.y; L[4 * j + 2] = v.z; L[4 * j + 3] = v.w; }
-                }
-            } else if (!mul) {
-#pragma unroll
-                for (int i = 0; i < 64; ++i) L[i] = 1.0f;
-            }
-            // the table is overwritten by TMA (async proxy) once all 8 warps have arrived: order the generic-proxy loads
-            // above before it — they may still sit in the LSU queue behind bank-conflicted wavefronts
-            tc5::fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(lempty + st);
-            ++luse;
-        };
-
-        // Cherry rows.  The warp owns a 32-row x 256-byte staging area; chunk ch (16 bytes) of row rr sits at chunk position
-        // (ch & 8) | ((ch ^ rr) & 7): the sixteen lanes that copy one row write two full 128-byte lines, and the eight threads of a
-        // quarter warp that later read chunk j of their OWN rows (LDS.128) hit eight different bank groups.
-        unsigned char *cstage = cherry_buf + (size_t)warp * T5_CHERRY_STAGE_BYTES;
-        const uint32_t cstage_s = tc5::smem_addr(cstage);
-        int ck = 0;                        // cherry (program order) whose rows are in flight / staged
-        auto prefetch_cherry = [&](int m, int k) {
-            const uint32_t cl = cherry_leaves[k];
-            const uint32_t myrow = (uint32_t)myids[(cl & 0xffu) * 128] * 65u + (uint32_t)myids[(cl >> 8) * 128];
-            const float *tab = a.cherrytab[m] + (size_t)k * ((size_t)T5_CHERRY_ROWS * 64);
-            const int half = lane >> 4, ch = lane & 15;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int rr = 2 * i + half;                      // the window (row of the staging area) this lane copies a chunk of
-                const uint32_t row = __shfl_sync(0xffffffffu, myrow, rr);
-                cp_async_16(cstage_s + rr * 256 + (((ch & 8) | ((ch ^ rr) & 7)) << 4), tab + (size_t)row * 64 + ch * 4);
-            }
-            cp_async_commit();
-        };
-        // L (= or *=) the staged cherry message of this thread's window; then starts the copy of the next cherry of the program
-        // (same ECM, or the other ECM's first one; the next pair's first one is started once its leaf ids are known)
-        auto take_cherry = [&](float (&L)[64], bool mul, int m) {
-            cp_async_wait_all();
-            __syncwarp();
-            const float4 *row = reinterpret_cast<const float4 *>(cstage + lane * 256);
+        uint32_t use = 0;
+        uint32_t taken = 0;           // running source number of this chain (over all pairs of the CTA)
+        const unsigned char *rstage = row_buf + (size_t)c * 2 * T5_ROW_STAGE_BYTES + (size_t)t * 256;
+        // L (= or *=) the staged message of this thread's window from the next source of the program
+        auto take_row = [&](float (&L)[64], bool mul) {
+            const uint32_t b = taken & 1;
+            mbar_wait(row_full + c * 2 + b, (taken >> 1) & 1);
+            const float4 *row = reinterpret_cast<const float4 *>(rstage + b * T5_ROW_STAGE_BYTES);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const float4 v = row[(j & 8) | ((j ^ lane) & 7)];
+                const float4 v = row[(j & 8) | ((j ^ t) & 7)];
                 if (mul) { L[4 * j] *= v.x; L[4 * j + 1] *= v.y; L[4 * j + 2] *= v.z; L[4 * j + 3] *= v.w; }
                 else { L[4 * j] = v.x; L[4 * j + 1] = v.y; L[4 * j + 2] = v.z; L[4 * j + 3] = v.w; }
             }
-            __syncwarp();
-            // the copy of the program's next cherry starts right away: it needs a whole step of lead time (issuing it only after
-            // this step's hand-over was measured 40 % slower at 8 Mi columns: the rows then come from DRAM as often as from L2)
-            if (++ck < a.n_cherry) prefetch_cherry(m, ck);
-            else { ck = 0; if (m == 0) prefetch_cherry(1, 0); }
-        };
-        auto fetch = [&](float (&L)[64], uint32_t src, bool mul, int m) {
-            if (src & T5_SRC_CHERRY) take_cherry(L, mul, m);
-            else gather(L, (int)src, mul);
+            mbar_arrive(row_empty + c * 2 + b);
+            ++taken;
         };
 
 #ifdef PCSF_TC5_TRACE
-        long long t_ids = 0, t_seq = 0, t_pro = 0, t_begin = clock64();
+        long long t_seq = 0, t_pro = 0, t_begin = clock64();
 #endif
         for (uint32_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-            // leaf codon ids of this thread's window
             const uint32_t u = pair * 256 + c * 128 + t;
-#ifdef PCSF_TC5_TRACE
-            long long tt0 = clock64();
-#endif
-            {
-                const uint32_t lw = a.uniq[u < n_unique ? u : n_unique - 1];
-                int64_t o; uint32_t strand;
-                if (a.ws.mode == 0) { o = a.ws.c0 + (lw >> 1); strand = lw & 1; }
-                else { o = a.ws.win_off[lw]; strand = 0; }
-                const uint8_t *p = a.ws.codes + o;
-                // 32 species at a time: all loads first (the byte stores below may alias anything as far as the compiler
-                // knows, which would otherwise serialise one DRAM round trip per species)
-                for (int s0 = 0; s0 < a.ws.nl; s0 += 32) {
-                    uint32_t v[32][3];
-#pragma unroll
-                    for (int k = 0; k < 32; ++k) {
-                        const uint8_t *q = p + (int64_t)(s0 + k < a.ws.nl ? s0 + k : s0) * a.ws.ld;
-                        v[k][0] = __ldg(q); v[k][1] = __ldg(q + 1); v[k][2] = __ldg(q + 2);
-                    }
-#pragma unroll
-                    for (int k = 0; k < 32; ++k)
-                        if (s0 + k < a.ws.nl)
-                            myids[(s0 + k) * 128] = (uint8_t)(strand ? codon_minus(v[k][0], v[k][1], v[k][2]) : codon_plus(v[k][0], v[k][1], v[k][2]));
-                }
-            }
-            if (a.n_cherry > 0) prefetch_cherry(0, 0);
-#ifdef PCSF_TC5_TRACE
-            t_ids += clock64() - tt0;
-#endif
             for (int m = 0; m < 2; ++m) {
                 float R[64];
                 int E = 0, sp = 0;
 #ifdef PCSF_TC5_TRACE
                 long long tt1 = clock64();
 #endif
-                fetch(R, a.start & 0xffu, false, m);
-                fetch(R, (a.start >> 8) & 0xffu, true, m);
+                take_row(R, false);
+                take_row(R, true);
 #ifdef PCSF_TC5_TRACE
                 long long tt2 = clock64();
                 t_pro += tt2 - tt1;
@@ -389,22 +406,21 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
 
                 for (int s = 0; s < a.n_steps; ++s, ++use) {
                     const uint32_t step = steps[s];
-                    const uint32_t post = (step >> 16) & 3u;
+                    const uint32_t post = (step >> 16) & 3u;           // MUL, PUSH_START or POP_MUL (prepare_tc5_program admits nothing else)
 #ifdef PCSF_TC5_TRACE
                     const bool first_seq = pair == blockIdx.x + 4 * gridDim.x && m == 0 && (t == 0);
 #endif
                     T5_TRACE(c, s, 0);
-                    // ---- while the GEMM runs: what the program multiplies in before the next GEMM — leaf messages from
-                    // their shared-memory tables, cherry messages from the staged table rows, or the waiting sibling partial
-                    // from the stack
+                    // ---- while the GEMM runs: what the program multiplies in before the next GEMM — leaf / cherry messages from
+                    // the staged table rows, or the waiting sibling partial from the stack
                     float L[64];
                     int Epop = 0;
                     if (post == T5_MUL) {
-                        fetch(L, step & 0xffu, false, m);
+                        take_row(L, false);
                     } else if (post == T5_PUSH_START) {
-                        fetch(L, step & 0xffu, false, m);
-                        fetch(L, (step >> 8) & 0xffu, true, m);
-                    } else if (post == T5_POP_MUL) {
+                        take_row(L, false);
+                        take_row(L, true);
+                    } else {
                         --sp;
                         const float4 *e4 = reinterpret_cast<const float4 *>(stk + (size_t)sp * T5_STACK_ENTRY_FLOATS);
 #pragma unroll
@@ -414,11 +430,21 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
                         }
                         Epop = __ldcg(reinterpret_cast<const int *>(stk + (size_t)sp * T5_STACK_ENTRY_FLOATS + 8192) + t);
                     }
+                    uint32_t dreg = lane_base + ((use & 1) ^ 1) * 128;           // D_s; A_{s+1} overwrites it in place
+                    asm volatile("" : "+r"(dreg));                               // in a register before the wait, not after it
                     T5_TRACE(c, s, 1);
                     mbar_wait(d_ready + c, use & 1);
                     T5_TRACE(c, s, 2);
                     tc5::fence_after_sync();
-                    const uint32_t dreg = lane_base + ((use & 1) ^ 1) * 128;     // D_s; A_{s+1} overwrites it in place
+                    // Any power of two is an exact scale, so the normalisation does not have to wait for this message's own maximum:
+                    // every entry is <= the largest entry of the A it was computed from (rows of P sum to <= 1), hence the exponent of
+                    // that previous maximum brings the message back to O(1), and how far below 1 the factors multiplied in push it is
+                    // corrected one step later.  The scale goes in BEFORE anything small is multiplied in: two lagging factors (a cherry
+                    // row is the product of two leaf columns) must not meet below FP32's range.
+                    const int e = amax_prev > 0.f ? (int)((__float_as_uint(amax_prev) >> 23) & 0xff) - 127 : 0;
+                    const float sc = __uint_as_float((uint32_t)(127 - e) << 23);
+                    const float2 sc2 = make_float2(sc, sc);
+                    E += e;
                     if (post == T5_PUSH_START || s + 1 == a.n_steps) {
                         // the message itself is needed (pushed onto the stack / dotted with pi): load all of it
                         {
@@ -431,10 +457,10 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
                             // msg = D[0:64] + D[64:128]
 #pragma unroll
                             for (int i = 0; i < 32; i += 2) {
-                                const float2 v0 = __fadd2_rn(make_float2(__uint_as_float(x0[i]), __uint_as_float(x0[i + 1])),
-                                                             make_float2(__uint_as_float(y0[i]), __uint_as_float(y0[i + 1])));
-                                const float2 v1 = __fadd2_rn(make_float2(__uint_as_float(x1[i]), __uint_as_float(x1[i + 1])),
-                                                             make_float2(__uint_as_float(y1[i]), __uint_as_float(y1[i + 1])));
+                                const float2 v0 = __fmul2_rn(__fadd2_rn(make_float2(__uint_as_float(x0[i]), __uint_as_float(x0[i + 1])),
+                                                                        make_float2(__uint_as_float(y0[i]), __uint_as_float(y0[i + 1]))), sc2);
+                                const float2 v1 = __fmul2_rn(__fadd2_rn(make_float2(__uint_as_float(x1[i]), __uint_as_float(x1[i + 1])),
+                                                                        make_float2(__uint_as_float(y1[i]), __uint_as_float(y1[i + 1]))), sc2);
                                 R[i] = v0.x; R[i + 1] = v0.y; R[32 + i] = v1.x; R[32 + i + 1] = v1.y;
                             }
                         }
@@ -443,12 +469,12 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
                             const int Epush = E;
                             E = 0;
                             split_and_arrive(L, dreg);
-                                        float4 *e4 = reinterpret_cast<float4 *>(stk + (size_t)sp * T5_STACK_ENTRY_FLOATS);
+                            float4 *e4 = reinterpret_cast<float4 *>(stk + (size_t)sp * T5_STACK_ENTRY_FLOATS);
 #pragma unroll
                             for (int j = 0; j < 16; ++j) __stcg(e4 + j * 128 + t, make_float4(R[4 * j], R[4 * j + 1], R[4 * j + 2], R[4 * j + 3]));
                             __stcg(reinterpret_cast<int *>(stk + (size_t)sp * T5_STACK_ENTRY_FLOATS + 8192) + t, Epush);
                             ++sp;
-                        } else if (post == T5_MUL || post == T5_POP_MUL) {
+                        } else {
 #pragma unroll
                             for (int i = 0; i < 64; i += 2) {
                                 const float2 v = __fmul2_rn(make_float2(R[i], R[i + 1]), make_float2(L[i], L[i + 1]));
@@ -457,17 +483,9 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
                             E += Epop;
                         }
                     } else {
-                        // Streamed hand-over.  Any power of two is an exact scale, so the normalisation does not have to wait
-                        // for this message's own maximum: every entry is <= the largest entry of the A it was computed from
-                        // (rows of P sum to <= 1, leaf and sibling factors are <= the scale they carry), hence the exponent of
-                        // that previous maximum keeps the new A below 2, and how far below is corrected one step later.  Without
-                        // a separate max pass the scale is folded into the combine (streaming the TMEM loads in two halves was measured slower:
-                        // a second tcgen05.wait::ld round trip costs more than the overlap gains, 114 against 97 ms).
-                        const bool mul = post == T5_MUL || post == T5_POP_MUL;
-                        const int e = amax_prev > 0.f ? (int)((__float_as_uint(amax_prev) >> 23) & 0xff) - 127 : 0;
-                        const float sc = __uint_as_float((uint32_t)(127 - e) << 23);
-                        const float2 sc2 = make_float2(sc, sc);
-                        E += e + (mul ? Epop : 0);
+                        // Streamed hand-over: alpha_parent = msg * L becomes A_{s+1} without a separate max pass (one tcgen05.wait::ld
+                        // round trip; streaming the TMEM loads in two halves was measured slower, 114 against 97 ms)
+                        E += Epop;
                         float amax = 0.f;
                         {
                             uint32_t x0[32], y0[32], x1[32], y1[32];
@@ -482,12 +500,10 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
                                                        make_float2(__uint_as_float(y0[i]), __uint_as_float(y0[i + 1])));
                                 float2 v1 = __fadd2_rn(make_float2(__uint_as_float(x1[i]), __uint_as_float(x1[i + 1])),
                                                        make_float2(__uint_as_float(y1[i]), __uint_as_float(y1[i + 1])));
-                                if (mul) {
-                                    v0 = __fmul2_rn(v0, make_float2(L[i], L[i + 1]));
-                                    v1 = __fmul2_rn(v1, make_float2(L[32 + i], L[32 + i + 1]));
-                                }
                                 v0 = __fmul2_rn(v0, sc2);
                                 v1 = __fmul2_rn(v1, sc2);
+                                v0 = __fmul2_rn(v0, make_float2(L[i], L[i + 1]));
+                                v1 = __fmul2_rn(v1, make_float2(L[32 + i], L[32 + i + 1]));
                                 amax = fmaxf(amax, fmaxf(fmaxf(v0.x, v0.y), fmaxf(v1.x, v1.y)));
                                 R[i] = v0.x; R[i + 1] = v0.y; R[32 + i] = v1.x; R[32 + i + 1] = v1.y;
                             }
@@ -496,9 +512,13 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
                         for (int h = 0; h < 4; ++h) {
                             uint32_t hi[16], lo[16];
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {
+                            for (int i = 0; i < 16; i += 2) {
                                 hi[i] = __float_as_uint(R[16 * h + i]) & 0xffffe000u;
-                                lo[i] = __float_as_uint(R[16 * h + i] - __uint_as_float(hi[i]));
+                                hi[i + 1] = __float_as_uint(R[16 * h + i + 1]) & 0xffffe000u;
+                                const float2 l = __fadd2_rn(make_float2(R[16 * h + i], R[16 * h + i + 1]),
+                                                            make_float2(-__uint_as_float(hi[i]), -__uint_as_float(hi[i + 1])));
+                                lo[i] = __float_as_uint(l.x);
+                                lo[i + 1] = __float_as_uint(l.y);
                             }
                             if (h == 2) {
                                 tc5::wait_st();
@@ -512,7 +532,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
                         tc5::fence_before_sync();
                         mbar_arrive(a_ready + 2 * c + 1);
                         amax_prev = amax;
-                            }
+                    }
                     T5_TRACE(c, s, 3);
                 }
                 // z = pi . alpha_root (fixed_lik.hpp:159-163), log z with the exponents taken out so far
@@ -521,7 +541,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
                     double z = 0.0;
 #pragma unroll
                     for (int i = 0; i < 64; ++i) z += pi[i] * (double)R[i];
-                    if (u < n_unique) a.logz[m][u] = log(z) + (double)E * 0.6931471805599453;
+                    if (u < n_unique) (m ? a.logz[1] : a.logz[0])[u] = log(z) + (double)E * 0.6931471805599453;
                 }
 #ifdef PCSF_TC5_TRACE
                 t_seq += clock64() - tt2;
@@ -530,8 +550,8 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
         }
 #ifdef PCSF_TC5_TRACE
         if ((blockIdx.x == 0 || blockIdx.x == 77) && t == 0)
-            printf("T5 cta %d chain %d: total %lld cycles, ids %lld, prologue gathers %lld, steps+END %lld, pairs %u\n", blockIdx.x, c,
-                   clock64() - t_begin, t_ids, t_pro, t_seq, (npairs - blockIdx.x + gridDim.x - 1) / gridDim.x);
+            printf("T5 cta %d chain %d: total %lld cycles, prologue gathers %lld, steps+END %lld, pairs %u\n", blockIdx.x, c,
+                   clock64() - t_begin, t_pro, t_seq, (npairs - blockIdx.x + gridDim.x - 1) / gridDim.x);
 #endif
     }
 #ifdef PCSF_TC5_TRACE

@@ -53,10 +53,15 @@ struct Interp {
     const ModelHost &m;
     const EcmHost &e;
     const uint8_t *ids;
-    size_t leaf_pos = 0, cherry_pos = 0;
+    size_t leaf_pos = 0, cherry_pos = 0, src_pos = 0;
     bool f32;
     Interp(const ModelHost &mm, const EcmHost &ee, const uint8_t *i, bool f) : m(mm), e(ee), ids(i), f32(f) {}
     void source(uint32_t s, double *out) {
+        const Tc5Src &d = m.tc5_srcs[src_pos++];          // the kernel walks this list: it must describe the same source
+        if ((s & T5_SRC_CHERRY) ? (d.l2 == 0xff || d.cherry != (s & 0x7fu) || d.l1 != (m.tc5_cherry_leaves[d.cherry] & 0xff) ||
+                                   d.l2 != (m.tc5_cherry_leaves[d.cherry] >> 8))
+                                : (d.l2 != 0xff || d.l1 != s))
+            host::die("source list out of step with the program");
         if (s & T5_SRC_CHERRY) {
             const size_t k = cherry_pos++;
             if ((s & 0x7fu) != k) host::die("cherry consumed out of table order");
@@ -137,7 +142,7 @@ struct Interp {
             if (((w & T5_END) != 0) != (s + 1 == m.tc5_steps.size())) host::die("END flag");
             E += renorm(R);
         }
-        if (!stack.empty() || leaf_pos != m.tc5_leaf_order.size() || cherry_pos != m.tc5_cherries.size()) host::die("program left-overs");
+        if (!stack.empty() || leaf_pos != m.tc5_leaf_order.size() || cherry_pos != m.tc5_cherries.size() || src_pos != m.tc5_srcs.size()) host::die("program left-overs");
         double z = 0.0;
         for (int a = 0; a < 64; ++a) z += e.pi[a] * R[a];
         return std::log(z) + (double)E * 0.6931471805599453;

@@ -1,6 +1,7 @@
 """Runs k_prune_tc5 from the PCSF_TC5_TRACE build of the library (per-step clock64 timestamps of one CTA)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("PCSF_TC5_NIDS", "1")   # the trace buffer is 12 KB of static shared memory
 import numpy as np
 import torch
 from phylocsfpp_b200 import capi

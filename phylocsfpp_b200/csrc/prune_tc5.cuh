@@ -368,24 +368,38 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
                 // A = split(alpha): per-window normalisation by an exact power of two, then TF32 hi + lo (hi = the 19 bits
                 // the tensor core reads, lo = the exact remainder); hands the step to the MMA warp
                 float amax_prev = 0.f;          // largest entry of the A that was handed over last (in [1, 2), or 0)
-                auto split_and_arrive = [&](const float (&V)[64], uint32_t areg) {
-                    float mx = 0.f;
+                // normalise(V): V *= 2^-e with e the exponent of V's largest entry (a tree of 3-input maxima, not a 64-long chain);
+                // returns e and leaves the new maximum (in [1, 2), or 0) in vmax
+                auto normalise = [&](float (&V)[64], float &vmax) {
+                    float m4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                    for (int i = 0; i < 64; ++i) mx = fmaxf(mx, V[i]);
+                    for (int i = 0; i < 64; i += 8) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) m4[k] = fmaxf(m4[k], fmaxf(V[i + 2 * k], V[i + 2 * k + 1]));
+                    }
+                    const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
                     const int e = mx > 0.f ? (int)((__float_as_uint(mx) >> 23) & 0xff) - 127 : 0;
                     const float sc = __uint_as_float((uint32_t)(127 - e) << 23);
                     const float2 sc2 = make_float2(sc, sc);
-                    E += e;
-                    amax_prev = mx * sc;
+#pragma unroll
+                    for (int i = 0; i < 64; i += 2) {
+                        const float2 r = __fmul2_rn(make_float2(V[i], V[i + 1]), sc2);
+                        V[i] = r.x; V[i + 1] = r.y;
+                    }
+                    vmax = mx * sc;
+                    return e;
+                };
+                // store_A(V, areg): TF32 hi + lo of the (normalised) partial into TMEM, states 0..31 handed to the MMA warp first
+                auto store_A = [&](const float (&V)[64], uint32_t areg) {
 #pragma unroll
                     for (int h = 0; h < 4; ++h) {
                         uint32_t hi[16], lo[16];
 #pragma unroll
                         for (int i = 0; i < 16; i += 2) {
-                            const float2 r = __fmul2_rn(make_float2(V[16 * h + i], V[16 * h + i + 1]), sc2);
-                            hi[i] = __float_as_uint(r.x) & 0xffffe000u;
-                            hi[i + 1] = __float_as_uint(r.y) & 0xffffe000u;
-                            const float2 l = __fadd2_rn(r, make_float2(-__uint_as_float(hi[i]), -__uint_as_float(hi[i + 1])));
+                            hi[i] = __float_as_uint(V[16 * h + i]) & 0xffffe000u;
+                            hi[i + 1] = __float_as_uint(V[16 * h + i + 1]) & 0xffffe000u;
+                            const float2 l = __fadd2_rn(make_float2(V[16 * h + i], V[16 * h + i + 1]),
+                                                        make_float2(-__uint_as_float(hi[i]), -__uint_as_float(hi[i + 1])));
                             lo[i] = __float_as_uint(l.x);
                             lo[i + 1] = __float_as_uint(l.y);
                         }
@@ -402,7 +416,10 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
                     tc5::fence_before_sync();
                     mbar_arrive(a_ready + 2 * c + 1);
                 };
-                if (a.n_steps > 0) split_and_arrive(R, lane_base + (use & 1) * 128);
+                if (a.n_steps > 0) {
+                    E += normalise(R, amax_prev);
+                    store_A(R, lane_base + (use & 1) * 128);
+                }
 
                 for (int s = 0; s < a.n_steps; ++s, ++use) {
                     const uint32_t step = steps[s];
@@ -414,12 +431,15 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
                     // ---- while the GEMM runs: what the program multiplies in before the next GEMM — leaf / cherry messages from
                     // the staged table rows, or the waiting sibling partial from the stack
                     float L[64];
-                    int Epop = 0;
+                    int Epop = 0;                  // exponent that comes with L: of the popped partial / of the new chain's start
+                    float amax_start = 0.f;
                     if (post == T5_MUL) {
                         take_row(L, false);
                     } else if (post == T5_PUSH_START) {
+                        // the start of a new chain does not depend on the running GEMM: it is normalised here, in the GEMM's shadow
                         take_row(L, false);
                         take_row(L, true);
+                        Epop = normalise(L, amax_start);
                     } else {
                         --sp;
                         const float4 *e4 = reinterpret_cast<const float4 *>(stk + (size_t)sp * T5_STACK_ENTRY_FLOATS);
@@ -445,48 +465,57 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
                     const float sc = __uint_as_float((uint32_t)(127 - e) << 23);
                     const float2 sc2 = make_float2(sc, sc);
                     E += e;
-                    if (post == T5_PUSH_START || s + 1 == a.n_steps) {
-                        // the message itself is needed (pushed onto the stack / dotted with pi): load all of it
-                        {
-                            uint32_t x0[32], y0[32], x1[32], y1[32];
-                            tc5::ld32(dreg, x0);
-                            tc5::ld32(dreg + 64, y0);
-                            tc5::ld32(dreg + 32, x1);
-                            tc5::ld32(dreg + 96, y1);
-                            tc5::wait_ld();
-                            // msg = D[0:64] + D[64:128]
+                    if (post == T5_PUSH_START) {
+                        // The message is pushed onto the stack (brought back to O(1) first) and the new chain's start (already normalised,
+                        // in L) becomes the next GEMM's input.  D_s is read in two halves, each pushed straight from the registers it
+                        // was loaded into: with L live, all four tcgen05.ld at once would not fit into the register file (the second
+                        // wait::ld round trip costs ~150 cycles on 9 of 39 steps of 58mammals; the spills it replaces cost more)
+                        float4 *e4 = reinterpret_cast<float4 *>(stk + (size_t)sp * T5_STACK_ENTRY_FLOATS);
 #pragma unroll
-                            for (int i = 0; i < 32; i += 2) {
+                        for (int hh = 0; hh < 2; ++hh) {
+                            uint32_t x0[32], y0[32];
+                            tc5::ld32(dreg + 32 * hh, x0);
+                            tc5::ld32(dreg + 64 + 32 * hh, y0);
+                            tc5::wait_ld();
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
                                 const float2 v0 = __fmul2_rn(__fadd2_rn(make_float2(__uint_as_float(x0[i]), __uint_as_float(x0[i + 1])),
                                                                         make_float2(__uint_as_float(y0[i]), __uint_as_float(y0[i + 1]))), sc2);
-                                const float2 v1 = __fmul2_rn(__fadd2_rn(make_float2(__uint_as_float(x1[i]), __uint_as_float(x1[i + 1])),
-                                                                        make_float2(__uint_as_float(y1[i]), __uint_as_float(y1[i + 1]))), sc2);
-                                R[i] = v0.x; R[i + 1] = v0.y; R[32 + i] = v1.x; R[32 + i + 1] = v1.y;
+                                const float2 v1 = __fmul2_rn(__fadd2_rn(make_float2(__uint_as_float(x0[i + 2]), __uint_as_float(x0[i + 3])),
+                                                                        make_float2(__uint_as_float(y0[i + 2]), __uint_as_float(y0[i + 3]))), sc2);
+                                __stcg(e4 + (8 * hh + i / 4) * 128 + t, make_float4(v0.x, v0.y, v1.x, v1.y));
                             }
                         }
-                        if (post == T5_PUSH_START) {
-                            // the next GEMM's input is the new chain's start (already in L): hand it over first, then push the message
-                            const int Epush = E;
-                            E = 0;
-                            split_and_arrive(L, dreg);
-                            float4 *e4 = reinterpret_cast<float4 *>(stk + (size_t)sp * T5_STACK_ENTRY_FLOATS);
+                        __stcg(reinterpret_cast<int *>(stk + (size_t)sp * T5_STACK_ENTRY_FLOATS + 8192) + t, E);
+                        ++sp;
+                        E = Epop;
+                        amax_prev = amax_start;
+                        store_A(L, dreg);
+                    } else if (s + 1 == a.n_steps) {
+                        // the root: alpha_root = msg * L stays in R for the dot product with pi
+                        uint32_t x0[32], y0[32], x1[32], y1[32];
+                        tc5::ld32(dreg, x0);
+                        tc5::ld32(dreg + 64, y0);
+                        tc5::ld32(dreg + 32, x1);
+                        tc5::ld32(dreg + 96, y1);
+                        tc5::wait_ld();
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) __stcg(e4 + j * 128 + t, make_float4(R[4 * j], R[4 * j + 1], R[4 * j + 2], R[4 * j + 3]));
-                            __stcg(reinterpret_cast<int *>(stk + (size_t)sp * T5_STACK_ENTRY_FLOATS + 8192) + t, Epush);
-                            ++sp;
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 64; i += 2) {
-                                const float2 v = __fmul2_rn(make_float2(R[i], R[i + 1]), make_float2(L[i], L[i + 1]));
-                                R[i] = v.x; R[i + 1] = v.y;
-                            }
-                            E += Epop;
+                        for (int i = 0; i < 32; i += 2) {
+                            float2 v0 = __fmul2_rn(__fadd2_rn(make_float2(__uint_as_float(x0[i]), __uint_as_float(x0[i + 1])),
+                                                              make_float2(__uint_as_float(y0[i]), __uint_as_float(y0[i + 1]))), sc2);
+                            float2 v1 = __fmul2_rn(__fadd2_rn(make_float2(__uint_as_float(x1[i]), __uint_as_float(x1[i + 1])),
+                                                              make_float2(__uint_as_float(y1[i]), __uint_as_float(y1[i + 1]))), sc2);
+                            v0 = __fmul2_rn(v0, make_float2(L[i], L[i + 1]));
+                            v1 = __fmul2_rn(v1, make_float2(L[32 + i], L[32 + i + 1]));
+                            R[i] = v0.x; R[i + 1] = v0.y; R[32 + i] = v1.x; R[32 + i + 1] = v1.y;
                         }
+                        E += Epop;
                     } else {
                         // Streamed hand-over: alpha_parent = msg * L becomes A_{s+1} without a separate max pass (one tcgen05.wait::ld
                         // round trip; streaming the TMEM loads in two halves was measured slower, 114 against 97 ms)
                         E += Epop;
                         float amax = 0.f;
+                        float V[64];
                         {
                             uint32_t x0[32], y0[32], x1[32], y1[32];
                             tc5::ld32(dreg, x0);
@@ -505,32 +534,10 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
                                 v0 = __fmul2_rn(v0, make_float2(L[i], L[i + 1]));
                                 v1 = __fmul2_rn(v1, make_float2(L[32 + i], L[32 + i + 1]));
                                 amax = fmaxf(amax, fmaxf(fmaxf(v0.x, v0.y), fmaxf(v1.x, v1.y)));
-                                R[i] = v0.x; R[i + 1] = v0.y; R[32 + i] = v1.x; R[32 + i + 1] = v1.y;
+                                V[i] = v0.x; V[i + 1] = v0.y; V[32 + i] = v1.x; V[32 + i + 1] = v1.y;
                             }
                         }
-#pragma unroll
-                        for (int h = 0; h < 4; ++h) {
-                            uint32_t hi[16], lo[16];
-#pragma unroll
-                            for (int i = 0; i < 16; i += 2) {
-                                hi[i] = __float_as_uint(R[16 * h + i]) & 0xffffe000u;
-                                hi[i + 1] = __float_as_uint(R[16 * h + i + 1]) & 0xffffe000u;
-                                const float2 l = __fadd2_rn(make_float2(R[16 * h + i], R[16 * h + i + 1]),
-                                                            make_float2(-__uint_as_float(hi[i]), -__uint_as_float(hi[i + 1])));
-                                lo[i] = __float_as_uint(l.x);
-                                lo[i + 1] = __float_as_uint(l.y);
-                            }
-                            if (h == 2) {
-                                tc5::wait_st();
-                                tc5::fence_before_sync();
-                                mbar_arrive(a_ready + 2 * c);
-                            }
-                            tc5::st16(dreg + 16 * h, hi);
-                            tc5::st16(dreg + 64 + 16 * h, lo);
-                        }
-                        tc5::wait_st();
-                        tc5::fence_before_sync();
-                        mbar_arrive(a_ready + 2 * c + 1);
+                        store_A(V, dreg);
                         amax_prev = amax;
                     }
                     T5_TRACE(c, s, 3);

@@ -76,6 +76,10 @@ void pcsf_model_destroy(pcsf_model *m);
 void *pcsf_alloc_pinned(size_t bytes);
 void pcsf_free_pinned(void *p);
 
+/* CUDA devices visible to the process (0 without a driver or device).  The command line host deals chain groups to all of them by
+ * default, as the reference uses all cores by default (build_tracks.hpp:88, --threads). */
+int pcsf_device_count(void);
+
 /* Thread-local description of the last error returned on this thread. */
 const char *pcsf_last_error(void);
 int pcsf_abi_version(void);

@@ -19,6 +19,7 @@
 #include "mle.cuh"
 #include "omega.cuh"
 #include "prune_tc5.cuh"
+#include <nvtx3/nvToolsExt.h>
 
 using namespace pcsf;
 
@@ -51,6 +52,12 @@ struct DevBuf {
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// NVTX range around the host-side enqueue of one stage (nsys / ncu --nvtx group the launches by it)
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
 };
 
 struct pcsf_model {
@@ -272,6 +279,7 @@ static inline uint32_t next_pow2(uint64_t x) {
 static pcsf_status dedup_and_prune(pcsf_model *m, const WinSpace &ws, uint32_t nwin, bool dedup, bool want_anc, int prec /* 0 FP64 DMMA, 2 tcgen05 */,
                                    uint32_t *d_nuniq_slot, uint32_t *d_pattern_out, int64_t out_base,
                                    cudaStream_t st, float *ms_hash, float *ms_dedup, float *ms_prune) {
+    NvtxRange nvtx_("pcsf: keys + dedup + prune");
     const int TB = 256;
     const uint32_t nblk = (nwin + TB - 1) / TB;
     CK(m->uniq.reserve((size_t)nwin * 4));
@@ -400,6 +408,7 @@ static pcsf_status run_pack(pcsf_model *m, const uint8_t *d_seqs, int64_t L, int
     CK(cudaMemsetAsync(m->d_bad, 0, sizeof(int), st));
     const int64_t nvec = m->codes_ld / 16;
     dim3 grid((unsigned)std::min<int64_t>((nvec + 255) / 256, 65535), nl);
+    NvtxRange nvtx_("pcsf: pack");
     m->launches++; k_pack<<<grid, 256, 0, st>>>(d_seqs, L, ld, nl, m->codes.as<uint8_t>(), m->codes_ld, m->codes_ld, m->d_bad);
     CK(cudaGetLastError());
     return PCSF_OK;
@@ -407,6 +416,7 @@ static pcsf_status run_pack(pcsf_model *m, const uint8_t *d_seqs, int64_t L, int
 
 static pcsf_status run_bls(pcsf_model *m, int64_t L, int raw, double *d_out, cudaStream_t st) {
     if (L <= 0) return PCSF_OK;
+    NvtxRange nvtx_("pcsf: bls");
     const size_t sh = (size_t)std::max(1, m->host.bls_depth) * BLS_THREADS * 8;
     m->launches++; k_bls<<<(unsigned)((L + BLS_THREADS - 1) / BLS_THREADS), BLS_THREADS, sh, st>>>(
         m->codes.as<uint8_t>(), m->codes_ld, m->host.nl, L, m->d_bls_prog, (int)m->host.bls_inner.size(),
@@ -462,7 +472,9 @@ extern "C" pcsf_status pcsf_tracks_device(pcsf_model *m, const uint8_t *d_seqs, 
         const int64_t c1 = std::min(W_all, (c + 1) * m->chunk_cols);
         return std::min<int64_t>(L, ((c1 + 2 + 15) / 16) * 16);
     };
+    NvtxRange nvtx_("pcsf_tracks_device");
     if (seg) {
+        NvtxRange nvtx_h2d("pcsf: H2D segments");
         m->codes_ld = ((L + 16 + 15) / 16) * 16;
         CK(m->codes.reserve((size_t)m->codes_ld * m->host.nl));
         CK(cudaMemsetAsync(m->d_bad, 0, sizeof(int), st));
@@ -526,6 +538,7 @@ extern "C" pcsf_status pcsf_tracks_device(pcsf_model *m, const uint8_t *d_seqs, 
                                       2 * c0, st, &m->last.ms_hash, &m->last.ms_dedup, &m->last.ms_prune)))
                 return rc;
             if (m->timing) CK(cudaEventRecord(m->ev[0], st));
+            NvtxRange nvtx_sc("pcsf: scatter + D2H");
             m->launches++; k_scatter_tracks<<<(nwin + 255) / 256, 256, 0, st>>>(nwin, m->pidx.as<uint32_t>(), m->logz.as<double>(),
                                                                  m->logz.as<double>() + nwin, c0, d_plus, d_minus);
             CK(cudaGetLastError());
@@ -576,6 +589,7 @@ extern "C" pcsf_status pcsf_tracks_device_finish(pcsf_model *m, void *cuda_strea
 extern "C" pcsf_status pcsf_tracks(pcsf_model *m, const uint8_t *seqs, int64_t L, int64_t ld, uint32_t flags, double *plus,
                                    double *minus, double *bls, uint32_t *pattern_index, pcsf_tracks_stats *stats) {
     if (!m || L < 0 || ld < L || (L > 0 && !seqs)) return fail(PCSF_ERR_INVALID, "pcsf_tracks: bad argument");
+    NvtxRange nvtx_("pcsf_tracks (host buffers)");
     CK(cudaSetDevice(m->device));
     if (stats) *stats = pcsf_tracks_stats{};
     if (L == 0) return PCSF_OK;
@@ -624,6 +638,11 @@ extern "C" void *pcsf_alloc_pinned(size_t bytes) {
     return p;
 }
 extern "C" void pcsf_free_pinned(void *p) { if (p) cudaFreeHost(p); }
+extern "C" int pcsf_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
 
 // ---- score-msa -------------------------------------------------------------------------------------
 extern "C" pcsf_status pcsf_score_msa(pcsf_model *m, pcsf_strategy strategy, int32_t n_aln, const uint8_t *seqs,
@@ -632,6 +651,7 @@ extern "C" pcsf_status pcsf_score_msa(pcsf_model *m, pcsf_strategy strategy, int
         return fail(PCSF_ERR_INVALID, "pcsf_score_msa: bad argument");
     if (strategy != PCSF_STRATEGY_FIXED && strategy != PCSF_STRATEGY_MLE && strategy != PCSF_STRATEGY_OMEGA)
         return fail(PCSF_ERR_INVALID, "pcsf_score_msa: unknown strategy");
+    NvtxRange nvtx_("pcsf_score_msa");
     CK(cudaSetDevice(m->device));
     if (n_aln == 0) return PCSF_OK;
     const int nl = m->host.nl;

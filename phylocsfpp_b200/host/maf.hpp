@@ -183,6 +183,81 @@ public:
         }
     }
 
+    // The same parse, written straight into a caller-owned matrix: row s of the chain goes to dst + s * row_stride, c.ref_cols columns
+    // (the reference bases the chain logic counted from the `size` fields).  One pass over the text: per block the reference row (the
+    // first row of the model's species, build_chains() insists on that) gives the runs of kept columns, every other row is copied run
+    // by run, absent species are filled with 'N'.  Returns the columns written, or -1 if the text disagrees with the size fields
+    // (the caller then takes read_chain(), which measures the text as the reference does).
+    int64_t read_chain_into(const Chain &c, uint8_t *dst, int64_t row_stride, std::vector<uint8_t> *species_seen) const {
+        if (c.ref_id < 0) return 0;
+        const int nl = model_.nl();
+        const int64_t limit = c.ref_cols;
+        int64_t col = 0;
+        struct Row { int id; const char *seq; size_t len; };
+        std::vector<Row> rows;
+        std::vector<uint8_t> present(nl);
+        std::vector<std::pair<size_t, size_t>> runs;
+        std::string key;
+        for (size_t bi : c.blocks) {
+            const BlockMeta &b = blocks_[bi];
+            const char *p = mem_ + b.off, *end = mem_ + b.end;
+            rows.clear();
+            std::fill(present.begin(), present.end(), 0);
+            const Row *ref = nullptr;
+            while (p < end) {
+                const char *nlp = (const char *)memchr(p, '\n', (size_t)(end - p));
+                const char *le = nlp ? nlp : end;
+                if (*p == 's') {
+                    SLine s;
+                    if (parse_s_line(p, le, s)) {
+                        const char *dot = (const char *)memchr(s.ident, '.', (size_t)s.ident_len);
+                        const int sl = dot ? (int)(dot - s.ident) : s.ident_len;
+                        key.assign(s.ident, (size_t)sl);
+                        for (char &ch : key) ch = (char)tolower((unsigned char)ch);
+                        auto it = model_.seqid_to_phyloid.find(key);
+                        if (it != model_.seqid_to_phyloid.end()) {
+                            if (present[it->second]) die("alignment rows of different length in block at byte %zu", b.off);
+                            present[it->second] = 1;
+                            rows.push_back(Row{(int)it->second, s.seq, s.seq_len});
+                            if (species_seen) (*species_seen)[it->second] = 1;
+                        }
+                    }
+                }
+                p = le + 1;
+            }
+            for (const Row &r : rows) if (r.id == c.ref_id) { ref = &r; break; }
+            if (!ref) continue;                                   // a block without the reference species adds no column
+            const size_t alen = ref->len;
+            // runs of kept alignment columns: where the reference has a base (:631-669), up to the breakpoint cut
+            runs.clear();
+            int64_t kept = 0;
+            size_t i = 0;
+            while (i < alen && col + kept < limit) {
+                const char *gap = (const char *)memchr(ref->seq + i, '-', alen - i);
+                size_t e = gap ? (size_t)(gap - ref->seq) : alen;
+                if ((int64_t)(e - i) > limit - col - kept) e = i + (size_t)(limit - col - kept);
+                if (e > i) { runs.emplace_back(i, e); kept += (int64_t)(e - i); }
+                i = e;
+                while (i < alen && ref->seq[i] == '-') ++i;
+            }
+            if (c.keep_cols < 0 && i < alen) return -1;           // more reference bases in the text than the size fields announced
+            for (const Row &r : rows) {
+                if (r.len > alen) die("alignment rows of different length in block at byte %zu", b.off);
+                uint8_t *o = dst + (int64_t)r.id * row_stride + col;
+                for (const auto &run : runs) {
+                    const size_t a0 = std::min(run.first, r.len), a1 = std::min(run.second, r.len);
+                    if (a1 > a0) memcpy(o, r.seq + a0, a1 - a0);
+                    if (a1 - a0 < run.second - run.first) memset(o + (a1 - a0), 'N', (run.second - run.first) - (a1 - a0));   // short row: N (:603-611)
+                    o += run.second - run.first;
+                }
+            }
+            for (int i = 0; i < nl; ++i)
+                if (!present[i]) memset(dst + (int64_t)i * row_stride + col, 'N', (size_t)kept);
+            col += kept;
+        }
+        return col == limit ? col : -1;
+    }
+
 private:
     void scan_range(size_t from, size_t to, std::vector<BlockMeta> &out, std::set<std::string> &unres) const {
         // blocks whose "a " line starts in [from, to)

@@ -100,6 +100,28 @@ struct ModelPool {
     void destroy() { for (pcsf_model *m : all) pcsf_model_destroy(m); all.clear(); free_models.clear(); }
 };
 
+// Page-locked host buffer that only grows (25 % headroom): the matrices and score vectors of a worker thread are handed to
+// pcsf_tracks call after call, so the DMA engines copy them without a staging pass.
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    PinnedBuf() = default;
+    PinnedBuf(const PinnedBuf &) = delete;
+    ~PinnedBuf() { pcsf_free_pinned(p); }
+    template <class T> T *get(size_t n) {
+        const size_t bytes = n * sizeof(T);
+        if (bytes > cap) {
+            pcsf_free_pinned(p);
+            cap = bytes + bytes / 4 + 4096;
+            p = pcsf_alloc_pinned(cap);
+            if (!p) die("cannot allocate %zu bytes of page-locked memory: %s", cap, pcsf_last_error());
+        }
+        return reinterpret_cast<T *>(p);
+    }
+};
+
+int default_gpus() { return std::max(1, pcsf_device_count()); }
+
 // one pool per GPU, filled in parallel (model preparation is host work: eigensystem + all P(t) + uploads)
 void make_pools(const Model &model, int gpus, int per_gpu, std::vector<std::unique_ptr<ModelPool>> &pools) {
     std::vector<pcsf_model *> ms((size_t)gpus * per_gpu);
@@ -153,7 +175,7 @@ int main_build_tracks(int argc, char **argv) {
     // the reference reads --power-threshold with get_bool (build_tracks.hpp:416-417): anything but 1/true/one gives 0
     const float threshold = a.has("power-threshold") ? (a.boolean("power-threshold", false) ? 1.0f : 0.0f) : 0.1f;
     const int threads = std::max(1, a.integer("threads", (int)std::thread::hardware_concurrency()));
-    const int gpus = std::max(1, a.integer("gpus", 1));
+    const int gpus = std::max(1, a.integer("gpus", default_gpus()));          // all visible devices unless told otherwise
     const uint32_t pflag = precision_flag(a);
 
     Model model;
@@ -216,6 +238,8 @@ int main_build_tracks(int argc, char **argv) {
     sink.resize(total_chains);
     std::atomic<size_t> next{0};
     std::atomic<int64_t> cols{0};
+    std::vector<std::atomic<int64_t>> gpu_cols(gpus);          // reference columns scored per device (the deal is group gi -> GPU gi mod gpus)
+    for (auto &g : gpu_cols) g = 0;
     std::mutex gpu_time_mu;
     // back-pressure: the workers run at most this many reference columns ahead of the writer (their finished text waits in memory,
     // about 16 bytes per column for the seven files)
@@ -227,8 +251,9 @@ int main_build_tracks(int argc, char **argv) {
     for (int t = 0; t < threads; ++t)
         workers.emplace_back([&, t] {
                 std::vector<Alignment> alns;
-                std::vector<uint8_t> mat;
-                std::vector<double> plus, minus, bls;
+                PinnedBuf mat_buf, plus_buf, minus_buf, bls_buf;
+                const uint8_t *src = nullptr;
+                double *plus = nullptr, *minus = nullptr, *bls = nullptr;
                 double my_gpu = 0.0, my_parse = 0.0, my_fmt = 0.0;
                 auto now = [] { return std::chrono::steady_clock::now(); };
                 auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
@@ -243,30 +268,46 @@ int main_build_tracks(int argc, char **argv) {
                     const std::vector<MafFile::Chain> &chains = maf.chains();
                     const size_t c0 = grp.c0, c1 = grp.c1, chain0 = fctx[grp.file].chain0;
                     alns.resize(c1 - c0);
+                    // The chains of the group side by side in one page-locked [nl][Ltot] matrix, parsed straight into it (the column
+                    // count of a chain is known from the scan: its reference bases).  A chain whose text disagrees with its size
+                    // fields falls back to the measuring parser, for the whole group.
                     int64_t Ltot = 0;
                     std::vector<int64_t> col0(c1 - c0);
-                    for (size_t ci = c0; ci < c1; ++ci) {
-                        maf.read_chain(chains[ci], alns[ci - c0], &seen[t]);
-                        col0[ci - c0] = Ltot;
-                        Ltot += alns[ci - c0].L;
+                    for (size_t ci = c0; ci < c1; ++ci) { col0[ci - c0] = Ltot; Ltot += chains[ci].ref_id < 0 ? 0 : chains[ci].ref_cols; }
+                    uint8_t *mat = mat_buf.get<uint8_t>((size_t)nl * std::max<int64_t>(Ltot, 1));
+                    bool direct = true;
+                    for (size_t ci = c0; ci < c1 && direct; ++ci) {
+                        const MafFile::Chain &c = chains[ci];
+                        Alignment &aln = alns[ci - c0];
+                        aln.start_pos = c.start_pos; aln.chrom_len = c.chrom_len; aln.strand = c.strand; aln.chrom = c.chrom;
+                        aln.seqs.clear();
+                        aln.L = maf.read_chain_into(c, mat + col0[ci - c0], Ltot, &seen[t]);
+                        if (aln.L < 0) direct = false;
+                    }
+                    if (!direct) {
+                        Ltot = 0;
+                        for (size_t ci = c0; ci < c1; ++ci) {
+                            maf.read_chain(chains[ci], alns[ci - c0], &seen[t]);
+                            col0[ci - c0] = Ltot;
+                            Ltot += alns[ci - c0].L;
+                        }
+                        mat = mat_buf.get<uint8_t>((size_t)nl * std::max<int64_t>(Ltot, 1));
+                        for (size_t k = 0; k < c1 - c0; ++k)
+                            for (int s = 0; s < nl; ++s)
+                                if (alns[k].L) memcpy(mat + (size_t)s * Ltot + col0[k], alns[k].seqs.data() + (size_t)s * alns[k].L, (size_t)alns[k].L);
                     }
                     if (Ltot > 0) {
-                        const uint8_t *src = alns[0].seqs.data();
-                        if (c1 - c0 > 1) {
-                            mat.resize((size_t)nl * Ltot);
-                            for (size_t k = 0; k < c1 - c0; ++k)
-                                for (int s = 0; s < nl; ++s)
-                                    if (alns[k].L) memcpy(mat.data() + (size_t)s * Ltot + col0[k], alns[k].seqs.data() + (size_t)s * alns[k].L, (size_t)alns[k].L);
-                            src = mat.data();
-                        }
-                        plus.resize((size_t)std::max<int64_t>(Ltot - 2, 0)); minus.resize(plus.size()); bls.resize((size_t)Ltot);
+                        src = mat;
+                        plus = plus_buf.get<double>((size_t)std::max<int64_t>(Ltot - 2, 1));
+                        minus = minus_buf.get<double>((size_t)std::max<int64_t>(Ltot - 2, 1));
+                        bls = bls_buf.get<double>((size_t)Ltot);
                         my_parse += secs(p0, now());
                         ModelPool &pool = *pools[gi % gpus];
                         pcsf_model *dm = pool.acquire();
                         const auto g0 = now();
                         pcsf_tracks_stats cs{};
                         const pcsf_status st = pcsf_tracks(dm, src, Ltot, Ltot, PCSF_TRACKS_BLS | (raw ? PCSF_TRACKS_SCORES : 0) | pflag,
-                                                           plus.data(), minus.data(), bls.data(), nullptr, &cs);
+                                                           plus, minus, bls, nullptr, &cs);
                         my_gpu += secs(g0, now());
                         if (dev_timing) {
                             std::lock_guard<std::mutex> g(gpu_time_mu);
@@ -277,6 +318,7 @@ int main_build_tracks(int argc, char **argv) {
                         if (st == PCSF_ERR_BAD_CHAR) { fprintf(stderr, "%s\n", pcsf_last_error()); exit(37); }      // translation.hpp:46-51
                         if (st != PCSF_OK) die("pcsf_tracks: %s", pcsf_last_error());
                         cols += Ltot;
+                        gpu_cols[gi % gpus] += Ltot;
                     }
                     const auto f0 = now();
                     for (size_t ci = c0; ci < c1; ++ci) {
@@ -284,7 +326,7 @@ int main_build_tracks(int argc, char **argv) {
                         const int64_t L = aln.L;
                         std::vector<std::string> text(7);
                         if (L > 0) {
-                            const double *pl = plus.data() + col0[ci - c0], *mi = minus.data() + col0[ci - c0], *bl = bls.data() + col0[ci - c0];
+                            const double *pl = plus + col0[ci - c0], *mi = minus + col0[ci - c0], *bl = bls + col0[ci - c0];
                             char hdr[512];
                             // power track (build_tracks.hpp:139-158)
                             {
@@ -382,10 +424,13 @@ int main_build_tracks(int argc, char **argv) {
     total_cols += cols;
     const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
     printf("\nDone!\n");
-    if (getenv("PCSF_HOST_STATS"))
+    if (getenv("PCSF_HOST_STATS")) {
+        std::string per_gpu;
+        for (int g = 0; g < gpus; ++g) per_gpu += (g ? ", " : "") + std::to_string((long long)gpu_cols[g]);
         printf("{\"columns\": %" PRId64 ", \"seconds\": %.3f, \"columns_per_s\": %.1f, \"threads\": %d, \"gpus\": %d, \"scan_seconds\": %.3f, "
-               "\"parse_seconds_sum\": %.3f, \"gpu_call_seconds_sum\": %.3f, \"format_seconds_sum\": %.3f}\n",
-               total_cols, wall, total_cols / wall, threads, gpus, t_scan, t_parse, t_gpu, t_format);
+               "\"parse_seconds_sum\": %.3f, \"gpu_call_seconds_sum\": %.3f, \"format_seconds_sum\": %.3f, \"columns_per_gpu\": [%s]}\n",
+               total_cols, wall, total_cols / wall, threads, gpus, t_scan, t_parse, t_gpu, t_format, per_gpu.c_str());
+    }
     if (dev_timing)
         printf("{\"ms_pack\": %.2f, \"ms_hash\": %.2f, \"ms_dedup\": %.2f, \"ms_prune\": %.2f, \"ms_scatter\": %.2f, \"ms_bls\": %.2f, \"windows\": %" PRId64
                ", \"unique\": %" PRId64 "}\n", dev_ms[0], dev_ms[1], dev_ms[2], dev_ms[3], dev_ms[4], dev_ms[5], dev_windows, dev_unique);
@@ -423,7 +468,7 @@ int main_score_msa(int argc, char **argv) {
         return -1;
     }
     const int threads = std::max(1, a.integer("threads", (int)std::thread::hardware_concurrency()));
-    const int gpus = std::max(1, a.integer("gpus", 1));
+    const int gpus = std::max(1, a.integer("gpus", default_gpus()));
     const int workers_n = std::min(threads, 2 * gpus);      // the per-call batch is the unit of GPU work; parsing runs inside the workers
 
     Model model;
@@ -576,6 +621,21 @@ int main_dump_alignments(int argc, char **argv) {
         Alignment aln;
         for (const MafFile::Chain &c : maf.chains()) {
             maf.read_chain(c, aln, nullptr);
+            // the build-tracks workers parse with read_chain_into (straight into their page-locked matrix, row stride != L): it has to
+            // give the same bytes whenever it accepts the chain
+            if (c.ref_id >= 0) {
+                const int64_t stride = c.ref_cols + 5;
+                std::vector<uint8_t> direct((size_t)model.nl() * stride, 0);
+                const int64_t L2 = maf.read_chain_into(c, direct.data(), stride, nullptr);
+                if (L2 >= 0) {
+                    if (L2 != aln.L) die("read_chain_into: %" PRId64 " columns, read_chain %" PRId64, L2, aln.L);
+                    for (int sidx = 0; sidx < model.nl(); ++sidx)
+                        if (aln.L && memcmp(direct.data() + (size_t)sidx * stride, aln.seqs.data() + (size_t)sidx * aln.L, (size_t)aln.L) != 0)
+                            die("read_chain_into differs from read_chain in row %d of the chain at %s:%" PRId64, sidx, aln.chrom.c_str(), aln.start_pos);
+                } else if (getenv("PCSF_REQUIRE_DIRECT")) {
+                    die("read_chain_into refused the chain at %s:%" PRId64, aln.chrom.c_str(), aln.start_pos);
+                }
+            }
             uint64_t h = 1469598103934665603ull;
             if (do_hash) for (uint8_t b : aln.seqs) { h ^= b; h *= 1099511628211ull; }
             printf("%s\t%" PRId64 "\t%" PRId64 "\t%c\t%" PRId64 "\t%016" PRIx64 "\n", aln.chrom.c_str(), aln.start_pos, aln.chrom_len, aln.strand, aln.L, h);

@@ -224,6 +224,41 @@ def test_build_tracks_cli_multiple_files(golden_dir, tmp_path):
         assert a == gzip.open(os.path.join(R, "tracks12." + n + ".gz"), "rb").read(), n
 
 
+@pytest.mark.gpu
+def test_build_tracks_cli_sharded_over_gpus(tmp_path):
+    """The sharded product path (north star: MAF blocks dealt to the GPUs, host-side ordered gather, no collective; reference analogue
+    build_tracks.hpp:88 job dealing and :27-53,245-259 ordered merge): --gpus 2 writes byte for byte what --gpus 1 writes, on both
+    precisions, and both devices did score columns.  Skipped on a single-device box."""
+    _need_bin()
+    import json
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from make_synth_maf import write_synth_maf
+    from phylocsfpp_b200.models import load_model
+    maf = os.path.join(str(tmp_path), "shard.maf")
+    write_synth_maf(maf, load_model("58mammals"), 400000, seed=77, mean_block=150, hole_p=1 / 60.0, ref_gap=0.01, alien_p=0.02, start0=800000)
+    env = dict(os.environ, PCSF_HOST_GROUP_COLS="30000", PCSF_HOST_STATS="1")
+    for prec in ("f64", "tc5"):
+        outs = []
+        for g in (1, 2):
+            out = os.path.join(str(tmp_path), f"{prec}_g{g}")
+            r = subprocess.run([BIN, "build-tracks", "--threads", "6", "--gpus", str(g), "--precision", prec, "--output", out, "58mammals", maf],
+                               check=True, capture_output=True, text=True, env=env)
+            st = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][0])
+            assert st["gpus"] == g and len(st["columns_per_gpu"]) == g and all(c > 0 for c in st["columns_per_gpu"]), st
+            outs.append(out)
+        for n in ["PhyloCSFpower.wig"] + [f"PhyloCSFRaw{s}{f}.wig" for s in "+-" for f in (1, 2, 3)]:
+            assert open(os.path.join(outs[0], n), "rb").read() == open(os.path.join(outs[1], n), "rb").read(), (prec, n)
+    # without --gpus the host uses every visible device
+    r = subprocess.run([BIN, "build-tracks", "--threads", "6", "--output", os.path.join(str(tmp_path), "dflt"), "58mammals", maf],
+                       check=True, capture_output=True, text=True, env=env)
+    st = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][0])
+    assert st["gpus"] == torch.cuda.device_count()
+
+
 def _py_hmm_smooth(params, runs):
     """Independent restatement of the smoothing stage in plain Python (reference src/create_tracks.hpp:86-158, 162-200, 226-235):
     params = (coding_prior, coding_codons, [w0, w1, w2], [n0, n1, n2]); runs = [(chrom, start, [scores])] -> wig text."""

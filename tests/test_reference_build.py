@@ -376,3 +376,54 @@ def test_model_info_matches_reference_binary(model_name):
         ours = subprocess.run([BIN, tool, "--model-info", model_name], capture_output=True, text=True, check=True).stdout
         ref = subprocess.run([REF, tool, "--model-info", model_name], capture_output=True, text=True, check=True).stdout
         assert ours == ref and model_name in ours and len(ours.splitlines()) > 5
+
+
+def _wig_values(path):
+    """(headers with their line numbers, values) of a wig file."""
+    heads, vals = [], []
+    with open(path) as fh:
+        for i, ln in enumerate(fh):
+            if ln.startswith("fixedStep"):
+                heads.append((i, ln))
+            else:
+                vals.append(float(ln))
+    return heads, np.array(vals)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model_name,cols,seed", [("58mammals", 60000, 51), ("100vertebrates", 50000, 52)])
+def test_acceptance_baseline_models_vs_reference_binary(tmp_path, model_name, cols, seed):
+    """North-star acceptance at BASELINE model size: build-tracks of the product against what the reference binary itself writes
+    for the same synthetic MAF (58mammals = config 3's model, 100vertebrates = config 4's; holes, reference gaps, unknown species
+    and a chain through the 1 Mb breakpoint).  FP64 path: seven wig files byte-identical.  tcgen05 path: identical fixedStep
+    headers at identical line numbers (gap / missing-species handling and wig positions are bit-exact), power track identical,
+    every PhyloCSF value within 1e-3 decibans (one unit of the last printed digit)."""
+    _need_ref()
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    os.environ["PCSF_SYNTH_CPU"] = "1"
+    from make_synth_maf import write_synth_maf
+    maf = os.path.join(str(tmp_path), "acc.maf")
+    write_synth_maf(maf, load_model(model_name), cols, seed=seed, mean_block=120, hole_p=1 / 40.0, ref_gap=0.02, alien_p=0.05,
+                    start0=1000000 - cols // 2)
+    ref_out = os.path.join(str(tmp_path), "ref")
+    subprocess.run([REF, "build-tracks", "--threads", str(os.cpu_count() or 8), "--output", ref_out, model_name, maf], check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    out64 = os.path.join(str(tmp_path), "f64")
+    subprocess.run([BIN, "build-tracks", "--threads", "4", "--output", out64, model_name, maf], check=True, capture_output=True)
+    for n in WIGS:
+        assert open(os.path.join(out64, n), "rb").read() == open(os.path.join(ref_out, n), "rb").read(), n
+    out5 = os.path.join(str(tmp_path), "tc5")
+    subprocess.run([BIN, "build-tracks", "--threads", "4", "--precision", "tc5", "--output", out5, model_name, maf], check=True,
+                   capture_output=True)
+    assert open(os.path.join(out5, WIGS[0]), "rb").read() == open(os.path.join(ref_out, WIGS[0]), "rb").read()
+    worst, nvals = 0.0, 0
+    for n in WIGS[1:]:
+        hr, vr = _wig_values(os.path.join(ref_out, n))
+        h5, v5 = _wig_values(os.path.join(out5, n))
+        assert h5 == hr, n
+        assert v5.shape == vr.shape and vr.size > 0
+        worst = max(worst, float(np.abs(v5 - vr).max()))
+        nvals += vr.size
+    print(f"{model_name}: tcgen05 path vs reference binary: max |delta| = {worst:.4f} decibans over {nvals} printed values")
+    assert worst <= 1e-3 + 1e-9

@@ -172,6 +172,259 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
 
 
+
+# ------------------------------------------------------------------------------------------------ legs beyond config 3
+SPECIES12 = "Human,Chimp,Mouse,Dog,Cow,Horse,Elephant,Armadillo,Rat,Rabbit,Cat,Megabat"
+
+
+def n_tc5_gemms(tree) -> int:
+    """GEMMs per pruning on the tcgen05 path: inner edges that are not cherries (a cherry's message is a table row)."""
+    c1, c2, nl, n = tree.child1, tree.child2, tree.nl, tree.n
+    cherries = sum(1 for i in range(nl, n - 1) if c1[c1[i]] < 0 and c1[c2[i]] < 0)
+    return (nl - 2) - cherries
+
+
+def _file_barrier(tag: str, rank: int, world: int, timeout: float = 3600.0):
+    """A barrier that leaves the GPUs idle (an NCCL barrier spins a kernel on every device): ranks drop a file, rank 0 waits for all."""
+    if world == 1:
+        return
+    base = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp", f"pcsf_bar_{os.environ.get('MASTER_PORT', '0')}_{tag}")
+    open(f"{base}.{rank}", "w").close()
+    t0 = time.time()
+    while not all(os.path.exists(f"{base}.{r}") for r in range(world)):
+        if time.time() - t0 > timeout:
+            raise SystemExit(f"file barrier {tag} timed out")
+        time.sleep(0.02)
+
+
+def leg_config4(total_cols, rank, world, local_rank, dist, torch, capi, precision_flag):
+    """BASELINE config 4: build-tracks 100vertebrates on a 250 M-column chromosome, STRONG-scaled: rank r owns the column range
+    [r T/N, (r+1) T/N), scores it in batches through pcsf_tracks (pinned host buffers, H2D + D2H inside) and writes the scores into
+    its range of one host array that rank 0 ends up holding in column order (OrderedHostBuffer: the host-side ordered gather, no
+    collective).  Timed region = all of that; max over ranks."""
+    from concurrent.futures import ThreadPoolExecutor
+    from phylocsfpp_b200.models import load_model
+    from phylocsfpp_b200.shard import OrderedHostBuffer, column_ranges
+    from phylocsfpp_b200.synth import synth_alignment
+    model = load_model("100vertebrates")
+    nl = model.nl
+    Bc = 1 << 22
+    lo, hi = column_ranges(total_cols, world, align=16)[rank]
+    dev = torch.device("cuda", local_rank)
+    dm = capi.DeviceModel(model, local_rank)
+    seqs = synth_alignment(model, Bc, seed=4321 + rank, device=dev)
+    ld = seqs.shape[1]
+    h_seqs = torch.empty((nl, ld), dtype=torch.uint8, pin_memory=True)
+    h_seqs.copy_(seqs)
+    del seqs
+    outs = [[torch.empty(Bc, dtype=torch.float64, pin_memory=True) for _ in range(3)] for _ in range(2)]
+    nbytes = 3 * total_cols * 8
+    path = os.path.join(OrderedHostBuffer.pick_dir(nbytes), f"pcsf_cfg4_{os.environ.get('MASTER_PORT', '0')}.bin")
+    if rank == 0:
+        OrderedHostBuffer(path, 3, total_cols, create=True).close()
+    if world > 1:
+        dist.barrier()
+    buf = OrderedHostBuffer(path, 3, total_cols)
+    lib = capi.load()
+    st = capi.TracksStats()
+    flags = capi.TRACKS_SCORES | capi.TRACKS_BLS | precision_flag
+    pool = ThreadPoolExecutor(1)
+
+    def run(do_store):
+        pending = [None, None]
+        k = 0
+        for c0 in range(lo, hi, Bc):
+            n = min(Bc, hi - c0)
+            o = outs[k & 1]
+            if pending[k & 1] is not None:
+                pending[k & 1].result()
+            capi._check(lib.pcsf_tracks(dm.h, h_seqs.data_ptr(), n, ld, flags, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), None, st))
+
+            def store(o=o, c0=c0, n=n):
+                buf.write(0, c0, o[0].numpy()[:max(n - 2, 0)])
+                buf.write(1, c0, o[1].numpy()[:max(n - 2, 0)])
+                buf.write(2, c0, o[2].numpy()[:n])
+            pending[k & 1] = pool.submit(store) if do_store else None
+            k += 1
+        for f in pending:
+            if f is not None:
+                f.result()
+        return k
+
+    # warm-up: one batch (allocations inside the library, page faults of the mapping are part of the timed run as in production)
+    hi_saved, hi = hi, min(hi, lo + Bc)
+    run(False)
+    hi = hi_saved
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    n_calls = run(True)
+    t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+    sec = float(t.item())
+    out = None
+    if rank == 0:
+        # every range has been written (first, last and a sample of columns of every rank's range are finite scores)
+        probe = []
+        for r in range(world):
+            rlo, rhi = column_ranges(total_cols, world, align=16)[r]
+            if rhi > rlo:
+                probe += [rlo, rhi - 1] + list(range(rlo, rhi, max(1, (rhi - rlo) // 50)))
+        bl = np.asarray(buf.arr[2, probe])
+        assert np.isfinite(bl).all() and (bl != 0).any()
+        out = {"workload": f"build-tracks 100vertebrates, {total_cols} synthetic columns (30% missing cells), strong-scaled over {world} GPU(s): "
+                           f"one column range per rank in batches of {Bc} (the rank's synthetic batch is re-used for every batch; 419 MB > L2), "
+                           "scores gathered in column order into one host array on rank 0 (file-backed mapping, no collective)",
+               "columns": total_cols, "seconds": sec, "columns_per_s": total_cols / sec, "n_gpus": world, "scaling": "strong",
+               "calls_per_rank": n_calls, "h2d_bytes": nl * total_cols, "d2h_bytes": 24 * total_cols,
+               "ordered_output": {"path_dir": os.path.dirname(path), "bytes": nbytes, "checksum_bls_probe": float(bl.sum())},
+               "precision": "tc5" if precision_flag else "f64", "timing": "wall clock around the whole leg, max over ranks (host work is part of it)"}
+    buf.close(unlink=(rank == 0))
+    pool.shutdown()
+    dm.close()
+    return out
+
+
+def leg_config5(total_aln, rank, world, local_rank, dist, torch, capi):
+    """BASELINE config 5: score-msa --strategy mle, 29mammals reduced to 12 species, synthetic single-block alignments of 30..600
+    columns (log-uniform), strong-scaled: every rank scores its share through pcsf_score_msa (host blob in, host scores out)."""
+    from phylocsfpp_b200.models import load_model
+    from phylocsfpp_b200.synth import synth_alignment
+    model = load_model("29mammals", SPECIES12)
+    nl = model.nl
+    dev = torch.device("cuda", local_rank)
+    dm = capi.DeviceModel(model, local_rank)
+    batch = 65536
+    share = (total_aln + world - 1) // world
+    n_calls = max(1, (share + batch - 1) // batch)
+    share = n_calls * batch
+    g = torch.Generator(device="cpu")
+    g.manual_seed(99 + rank)
+    lens = torch.exp(torch.rand(batch, generator=g, dtype=torch.float64) * (np.log(600.0) - np.log(30.0)) + np.log(30.0)).to(torch.int64)
+    starts = torch.cumsum(lens, 0) - lens
+    Ltot = int(lens.sum())
+    mat = synth_alignment(model, Ltot, seed=777 + rank, device=dev)[:, :Ltot]          # [nl, Ltot] on the device
+    lens_d, starts_d = lens.to(dev), starts.to(dev)
+    offs_d = starts_d * nl                                                             # alignment i is a contiguous [nl][len_i] block
+    aln_of_col = torch.repeat_interleave(torch.arange(batch, device=dev), lens_d)
+    col_in_aln = torch.arange(Ltot, device=dev) - starts_d[aln_of_col]
+    blob_d = torch.empty(nl * Ltot, dtype=torch.uint8, device=dev)
+    for s_ in range(nl):
+        blob_d[offs_d[aln_of_col] + s_ * lens_d[aln_of_col] + col_in_aln] = mat[s_]
+    blob = torch.empty(nl * Ltot, dtype=torch.uint8, pin_memory=True)
+    blob.copy_(blob_d)
+    del blob_d, mat, aln_of_col, col_in_aln
+    offs = (starts * nl).contiguous()
+    phylo = torch.empty(batch, dtype=torch.float32, pin_memory=True)
+    anc = torch.empty(batch, dtype=torch.float32, pin_memory=True)
+    bls = torch.empty(batch, dtype=torch.float32, pin_memory=True)
+    lib = capi.load()
+
+    def call():
+        capi._check(lib.pcsf_score_msa(dm.h, capi.STRATEGY_MLE, batch, blob.data_ptr(), offs.data_ptr(), lens.data_ptr(),
+                                       phylo.data_ptr(), anc.data_ptr(), bls.data_ptr()))
+
+    call()          # warm-up (scratch allocation)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_calls):
+        call()
+    t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sec = float(t.item())
+    stats = dm.score_msa_stats()
+    out = None
+    if rank == 0:
+        # one instrumented call: CUDA-event time per kernel -> rooflines of the batched P(t) construction and of the MLE pruning
+        dm.set_timing(True)
+        call()
+        ts = dm.score_msa_stats()
+        dm.set_timing(False)
+        n = model.tree.n
+        flop_expm = ts["evaluations"] * (n - 1) * (2 * 64 ** 3 + 64 ** 2)
+        codons = float((lens // 3).sum())
+        flop_prune = ts["evaluations"] / max(1, 2 * batch) * 2 * codons * flops_per_pruning(nl)      # evaluations x codons of the alignment (mean)
+        peak = 37.16
+        try:
+            peak = json.load(open(os.path.join(ROOT, "profiles", "peaks_fp64.json")))["micro"]["dmma_tflops"]
+        except Exception:
+            pass
+        finite = int(torch.isfinite(phylo).sum())
+        out = {"workload": f"score-msa --strategy mle --comp-anc 1 --species <12 of 29mammals>, {share * world} synthetic single-block alignments "
+                           f"of 30..600 columns (log-uniform, mean {Ltot / batch:.0f}), strong-scaled over {world} GPU(s) in calls of {batch} "
+                           "(the rank's batch is re-used for every call), host blob in / host scores out through pcsf_score_msa",
+               "alignments": share * world, "seconds": sec, "alignments_per_s": share * world / sec, "columns_per_s": Ltot * n_calls * world / sec,
+               "n_gpus": world, "scaling": "strong", "mean_evaluations_per_alignment": stats["evaluations"] / batch,
+               "rounds_per_call": stats["rounds"], "slots": stats["slots"], "finite_scores_in_last_batch": finite,
+               "roofline": {"k_mle_expm": {"bound": "tensor", "unit": "TFLOP/s", "flop": flop_expm, "ms": ts["ms_expm"],
+                                           "achieved": flop_expm / max(ts["ms_expm"], 1e-9) / 1e9, "peak": peak,
+                                           "frac": flop_expm / max(ts["ms_expm"], 1e-9) / 1e9 / peak,
+                                           "note": "(n-1)(2*64^3+64^2) flop per evaluation (SURVEY 8d), FP64 DMMA peak of profiles/peaks_fp64.json"},
+                            "k_prune<true>": {"bound": "tensor", "unit": "TFLOP/s", "flop": flop_prune, "ms": ts["ms_prune"],
+                                              "achieved": flop_prune / max(ts["ms_prune"], 1e-9) / 1e9, "peak": peak,
+                                              "frac": flop_prune / max(ts["ms_prune"], 1e-9) / 1e9 / peak},
+                            "ms_step": ts["ms_step"], "ms_plan": ts["ms_plan"]}}
+    dm.close()
+    return out
+
+
+def leg_cli(cols, rank, world, local_rank, torch):
+    """The drop-in command line on a config-3 shaped MAF file in tmpfs: phylocsf_b200 build-tracks --gpus N --precision tc5, MAF text
+    -> 7 wig files.  Rank 0 runs the process (it deals chain groups to all N devices itself); the other ranks keep their GPUs idle."""
+    import shutil
+    import tempfile
+    from phylocsfpp_b200.models import load_model
+    from phylocsfpp_b200.synth import synth_alignment
+    out = None
+    if rank == 0:
+        BIN = os.path.join(ROOT, "phylocsfpp_b200", "bin", "phylocsf_b200")
+        model = load_model("58mammals")
+        base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > 3 * 58 * cols else None
+        tmp = tempfile.mkdtemp(prefix="pcsf_cli_", dir=base)
+        try:
+            dev = torch.device("cuda", local_rank)
+            piece = 1 << 23
+            with open(os.path.join(tmp, "m.bin"), "wb") as fh:
+                rows = []
+                for c0 in range(0, cols, piece):
+                    n = min(piece, cols - c0)
+                    rows.append(synth_alignment(model, n, seed=5000 + c0 // piece, device=dev)[:, :n].cpu().numpy())
+                np.concatenate(rows, axis=1).tofile(fh)
+            del rows
+            torch.cuda.empty_cache()
+            maf = os.path.join(tmp, "cfg3.maf")
+            subprocess.run([BIN, "matrix-to-maf", "--chain", str(25_000_000), "58mammals", os.path.join(tmp, "m.bin"), str(cols), maf],
+                           check=True, capture_output=True)
+            os.unlink(os.path.join(tmp, "m.bin"))
+            threads = os.cpu_count() or 1
+            best = None
+            for rep in range(2):
+                t0 = time.perf_counter()
+                r = subprocess.run([BIN, "build-tracks", "--threads", str(threads), "--gpus", str(world), "--precision", "tc5", "--output",
+                                    os.path.join(tmp, "out"), "58mammals", maf], check=True, capture_output=True, text=True,
+                                   env=dict(os.environ, PCSF_HOST_STATS="1"))
+                dt = time.perf_counter() - t0
+                st = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][0])
+                if best is None or st["seconds"] < best[1]["seconds"]:
+                    best = (dt, st)
+            wig_bytes = sum(os.path.getsize(os.path.join(tmp, "out", f)) for f in os.listdir(os.path.join(tmp, "out")))
+            out = {"workload": f"phylocsf_b200 build-tracks --gpus {world} --precision tc5 --threads {threads} on a synthetic 58mammals MAF file "
+                               f"({cols} columns, {os.path.getsize(maf)} bytes, tmpfs) -> PhyloCSFpower.wig + 6 PhyloCSFRaw wigs ({wig_bytes} bytes)",
+                   "columns": cols, "tool_seconds": best[1]["seconds"], "columns_per_s": cols / best[1]["seconds"],
+                   "process_seconds": best[0], "columns_per_s_process": cols / best[0], "n_gpus": world, "host_threads": threads,
+                   "tool_stats": best[1], "note": "tool_seconds = models ready -> files written; process_seconds adds CUDA context + model preparation"}
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+    _file_barrier("cli", rank, world)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -185,6 +438,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-port", action="store_true", help="time the oracle port instead of the reference binary on the CPU legs")
     ap.add_argument("--no-dedup", action="store_true")
+    ap.add_argument("--config4-cols", type=int, default=250_000_000, help="columns of the strong-scaled 100vertebrates leg (0 = skip)")
+    ap.add_argument("--config5-alignments", type=int, default=1_000_000, help="alignments of the strong-scaled MLE leg (0 = skip)")
+    ap.add_argument("--cli-cols", type=int, default=1 << 24, help="columns of the MAF file of the command-line leg (0 = skip)")
     ap.add_argument("--precision", default="tc5", choices=["f64", "tc5"],
                     help="tc5: tcgen05/TMEM split-TF32 path (fastest path inside the 1e-3 deciban contract); "
                          "f64: FP64 DMMA path (parity anchor, byte-identical wig text)")
@@ -354,6 +610,7 @@ def main():
                             "columns_per_s_kernels_only": B / (1e-3 * sum(o[k] for k in ("ms_pack", "ms_hash", "ms_dedup", "ms_prune", "ms_scatter", "ms_bls")))}
         dm.set_timing(False)
 
+    out = None
     if rank == 0:
         F = flops_per_pruning(nl)
         n_prune_launch = max(1, tstats["n_chunks"])
@@ -392,7 +649,8 @@ def main():
             peak_source = ("dense TF32 tensor peak = cuBLAS TF32 GEMM 8192^3 measured on this pool (profiles/peaks_fp64.json; "
                            "MEASURED_PEAKS.json carries bf16 only: 1605 TFLOP/s burst, TF32 is half rate); `achieved` counts "
                            "ALGORITHMIC flops (one FP product per term), `executed_tflops` what the tensor pipe ran")
-            mult = (3.0 * 8192 * (nl - 2)) / F
+            # executed tensor flops: three TF32 products per GEMM edge; cherry edges are table rows (no tensor work)
+            mult = (3.0 * 8192 * n_tc5_gemms(model.tree)) / F
             executed = achieved * mult
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -438,8 +696,21 @@ def main():
                 out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": ncores, "kind": "port", "seconds": dt,
                                        "sample": f"first {S} columns of the step's batch, oracle port of the reference path, "
                                                  f"{ncores} processes"}
-        print(json.dumps(out), file=json_out, flush=True)
+    # ---- the other BASELINE configs and the command line, on the same box in the same run (all ranks take part)
     dm.close()
+    del seqs, plus, minus, bls, h_seqs, h_plus, h_minus, h_bls
+    torch.cuda.empty_cache()
+    pflag = capi.TRACKS_TC5 if args.precision == "tc5" else 0
+    legs = {}
+    if args.config4_cols > 0:
+        legs["config4"] = leg_config4(args.config4_cols, rank, world, local_rank, dist, torch, capi, pflag)
+    if args.config5_alignments > 0:
+        legs["config5"] = leg_config5(args.config5_alignments, rank, world, local_rank, dist, torch, capi)
+    if args.cli_cols > 0:
+        legs["cli"] = leg_cli(args.cli_cols, rank, world, local_rank, torch)
+    if rank == 0:
+        out.update(legs)
+        print(json.dumps(out), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

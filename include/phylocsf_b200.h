@@ -149,6 +149,16 @@ pcsf_status pcsf_score_msa(pcsf_model *m, pcsf_strategy strategy, int32_t n_aln,
 
 /* ---- introspection (used by the parity tests) -------------------------------------------------- */
 
+/* What the last pcsf_score_msa call with PCSF_STRATEGY_MLE did on this handle: `evaluations` counts lpr_leaves calls — (alignment,
+ * ECM, rho) triples, each one (n-1) x (2 x 64^3 + 64^2) flop of P(t) = exp(Qt) construction (PhyloModel_make, instance.hpp:449-646)
+ * plus one pruning pass over the alignment's codons.  The per-kernel CUDA-event times are filled only with pcsf_set_timing on. */
+typedef struct {
+    int64_t alignments, evaluations;
+    int32_t rounds, slots;
+    float ms_step, ms_plan, ms_expm, ms_prune;
+} pcsf_msa_stats;
+pcsf_status pcsf_score_msa_stats(const pcsf_model *m, pcsf_msa_stats *stats);
+
 /* Copies the model's host-side matrices: which in {0 coding, 1 non-coding}.
  * lambda[64], pi[64], P[(n-1)*64*64] row-major P_b[a][c] at rho = 1; any pointer may be NULL. */
 pcsf_status pcsf_model_get(const pcsf_model *m, int which, double *lambda, double *pi, double *P);

@@ -33,7 +33,7 @@ STRATEGY_OMEGA = 2
 EXPORTS = [
     "pcsf_model_create", "pcsf_model_destroy", "pcsf_last_error", "pcsf_abi_version", "pcsf_tracks",
     "pcsf_tracks_device", "pcsf_tracks_device_finish", "pcsf_set_chunk_columns", "pcsf_set_timing",
-    "pcsf_score_msa", "pcsf_model_get", "pcsf_alloc_pinned", "pcsf_free_pinned", "pcsf_device_count",
+    "pcsf_score_msa", "pcsf_model_get", "pcsf_alloc_pinned", "pcsf_free_pinned", "pcsf_device_count", "pcsf_score_msa_stats",
 ]
 
 
@@ -53,6 +53,14 @@ class TracksStats(C.Structure):
     _fields_ = [("n_windows", C.c_int64), ("n_unique", C.c_int64), ("n_chunks", C.c_int32), ("n_launches", C.c_int32),
                 ("ms_pack", C.c_float), ("ms_hash", C.c_float), ("ms_dedup", C.c_float), ("ms_prune", C.c_float),
                 ("ms_scatter", C.c_float), ("ms_bls", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class MsaStats(C.Structure):
+    _fields_ = [("alignments", C.c_int64), ("evaluations", C.c_int64), ("rounds", C.c_int32), ("slots", C.c_int32),
+                ("ms_step", C.c_float), ("ms_plan", C.c_float), ("ms_expm", C.c_float), ("ms_prune", C.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -89,6 +97,8 @@ def load():
     L.pcsf_score_msa.argtypes = [C.c_void_p, C.c_int, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p]
     L.pcsf_model_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pcsf_score_msa_stats.argtypes = [C.c_void_p, C.POINTER(MsaStats)]
+    L.pcsf_device_count.restype = C.c_int
     _lib = L
     return L
 
@@ -169,6 +179,11 @@ class DeviceModel:
     def tracks_device_finish(self, stream: int):
         st = TracksStats()
         _check(load().pcsf_tracks_device_finish(self.h, stream, C.byref(st)))
+        return st.as_dict()
+
+    def score_msa_stats(self):
+        st = MsaStats()
+        _check(load().pcsf_score_msa_stats(self.h, C.byref(st)))
         return st.as_dict()
 
     def score_msa(self, alignments, strategy: int = STRATEGY_FIXED, comp_anc: bool = True, comp_bls: bool = True):

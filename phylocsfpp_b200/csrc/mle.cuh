@@ -53,6 +53,15 @@ struct MleSlot {
     int64_t K, win0;
 };
 
+// What one mle_run did (pcsf_score_msa_stats): evaluations = lpr_leaves calls, i.e. (alignment, model, rho) triples, each costing
+// (n-1) x (2 x 64^3 + 64^2) flop of P(t) construction plus one pruning pass over the alignment's codons.  The per-kernel times are
+// CUDA-event times, collected only when pcsf_set_timing is on (the events serialise the rounds a little).
+struct MleStats {
+    int64_t alignments = 0, evaluations = 0;
+    int32_t rounds = 0, slots = 0;
+    float ms_step = 0.f, ms_plan = 0.f, ms_expm = 0.f, ms_prune = 0.f;
+};
+
 struct MleBatch {
     int n_aln;
     const int64_t *d_win_start, *d_col_start, *d_len;
@@ -164,7 +173,7 @@ __device__ inline bool fit_advance(MleSlot &s, double lo, double hi, double init
 // One thread per slot.  cand[i] = exp(log(lo) + U_i) (host-tabulated).  queue_head: next alignment to fit.
 // Uses __dadd_rn etc. only where the reference's order matters (sequential sums); contraction elsewhere is
 // harmless (the iterate sequence is compared at 1e-3 decibans / the reference's own CI tolerance).
-__global__ void k_mle_step(MleSlot *slots, int n_slots, int n_aln, int *queue_head, int *n_active,
+__global__ void k_mle_step(MleSlot *slots, int n_slots, int n_aln, int *queue_head, int *n_active, unsigned long long *n_evals,
                            const int64_t *__restrict__ win_start, const int64_t *__restrict__ len,
                            const double *__restrict__ logz, const double *__restrict__ ancw, const int *__restrict__ expm_err,
                            const double *__restrict__ cand, double lo, double hi, double init, int want_anc,
@@ -227,6 +236,7 @@ __global__ void k_mle_step(MleSlot *slots, int n_slots, int n_aln, int *queue_he
     }
     slots[si] = s;
     if (s.aln >= 0) atomicAdd(n_active, 1);
+    if (s.aln >= 0 && s.pending && n_evals) atomicAdd(n_evals, 1ull);
 }
 
 // Single block: tile descriptors for every slot with a pending evaluation.
@@ -400,7 +410,8 @@ inline MleSetup mle_prepare(const ModelHost &h, double lo, double hi) {
 template <class Buf>
 inline pcsf_status mle_run(const ModelHost &h, const MleBatch &b, double *const *d_eig, const float *d_bl,
                            const int32_t *d_program, const double *const *d_pi, const double *const *d_logpi, Buf &scratch,
-                           int sm_count, size_t prune_smem, int prune_nwarp, cudaStream_t st, std::string &err, int *launches) {
+                           int sm_count, size_t prune_smem, int prune_nwarp, cudaStream_t st, std::string &err, int *launches,
+                           MleStats *stats = nullptr, bool timing = false) {
     const double lo = 1e-2, hi = 10.0, init = 1.0;   // run.hpp:193-194
     const MleSetup su = mle_prepare(h, lo, hi);
     const int n_br = h.n - 1, n_gemm = (int)h.gemm_edges.size();
@@ -451,23 +462,50 @@ inline pcsf_status mle_run(const ModelHost &h, const MleBatch &b, double *const 
     pa.logz[0] = d_logz;
     pa.anc[0] = b.want_anc ? d_ancw : nullptr;
 
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (timing && stats) for (auto &e : ev) MCK(cudaEventCreate(&e));
+    struct EvGuard { cudaEvent_t *ev; ~EvGuard() { for (int i = 0; i < 5; ++i) if (ev[i]) cudaEventDestroy(ev[i]); } } ev_guard{ev};
+    if (stats) { *stats = MleStats{}; stats->alignments = b.n_aln; stats->slots = n_slots; }
+    unsigned long long *d_evals = reinterpret_cast<unsigned long long *>(d_ctr + 4);
+    auto finish_stats = [&]() -> cudaError_t {
+        if (!stats) return cudaSuccess;
+        unsigned long long ne = 0;
+        cudaError_t e = cudaMemcpyAsync(&ne, d_evals, 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        stats->evaluations = (int64_t)ne;
+        return e;
+    };
     // every evaluation round: step -> (host reads n_active) -> plan -> expm -> prune
     const int max_rounds = 2 * (3 + MLE_MAX_TRIES + 1 + 4 + 250) * ((b.n_aln + n_slots - 1) / n_slots) + 8;
     for (int round = 0; round < max_rounds; ++round) {
         MCK(cudaMemsetAsync(d_ctr + 1, 0, 4, st));
-        k_mle_step<<<(n_slots + 127) / 128, 128, 0, st>>>(d_slots, n_slots, b.n_aln, d_ctr, d_ctr + 1, b.d_win_start, b.d_len,
+        if (ev[0]) MCK(cudaEventRecord(ev[0], st));
+        k_mle_step<<<(n_slots + 127) / 128, 128, 0, st>>>(d_slots, n_slots, b.n_aln, d_ctr, d_ctr + 1, d_evals, b.d_win_start, b.d_len,
                                                          d_logz, d_ancw, d_err, d_cand, lo, hi, init, b.want_anc ? 1 : 0,
                                                          b.d_phylo, b.d_anc);
+        if (ev[0]) MCK(cudaEventRecord(ev[1], st));
         int n_active = 0;
         MCK(cudaMemcpyAsync(&n_active, d_ctr + 1, 4, cudaMemcpyDeviceToHost, st));
         MCK(cudaStreamSynchronize(st));
         if (launches) *launches += 1;
-        if (n_active == 0) return PCSF_OK;
+        if (stats) stats->rounds = round;
+        if (n_active == 0) { MCK(finish_stats()); return PCSF_OK; }
         MCK(cudaMemsetAsync(d_err, 0, (size_t)n_slots * 4, st));
         k_mle_plan<<<1, 1024, 0, st>>>(d_slots, n_slots, d_p, slot_stride, leaf_off, tw, d_tiles, reinterpret_cast<uint32_t *>(d_ctr + 2));
+        if (ev[0]) MCK(cudaEventRecord(ev[2], st));
         k_mle_expm<<<n_slots * n_br, 128, 0, st>>>(d_slots, n_br, h.nl, d_bl, d_eig[0], d_eig[1], d_e2g, d_p, slot_stride, leaf_off, d_err);
+        if (ev[0]) MCK(cudaEventRecord(ev[3], st));
         k_prune<true><<<sm_count, (prune_nwarp + 1) * 32, prune_smem, st>>>(pa);
         MCK(cudaGetLastError());
+        if (ev[0]) {
+            MCK(cudaEventRecord(ev[4], st));
+            MCK(cudaEventSynchronize(ev[4]));
+            float t;
+            MCK(cudaEventElapsedTime(&t, ev[0], ev[1])); stats->ms_step += t;
+            MCK(cudaEventElapsedTime(&t, ev[1], ev[2])); stats->ms_plan += t;
+            MCK(cudaEventElapsedTime(&t, ev[2], ev[3])); stats->ms_expm += t;
+            MCK(cudaEventElapsedTime(&t, ev[3], ev[4])); stats->ms_prune += t;
+        }
         if (launches) *launches += 3;
     }
     err = "MLE did not converge within the reference's iteration limits (internal error)";

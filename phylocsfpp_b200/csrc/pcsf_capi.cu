@@ -85,6 +85,7 @@ struct pcsf_model {
     float *d_tc5_scratch = nullptr;      // stack spill of k_prune_tc5: [sm_count][2][max_stack][T5_STACK_ENTRY_FLOATS]
     size_t prune_tc5_smem = 0;
     int tc5_nstage = 2, tc5_nids = 1;
+    MleStats msa_stats;                  // of the last MLE score-msa call
     DevBuf tc5_ids;                      // codon ids of the unique windows, [pairs][2][nl][128] (k_tc5_ids)
     int32_t *d_program = nullptr;
     BlsInner *d_bls_prog = nullptr;
@@ -243,6 +244,13 @@ extern "C" void pcsf_model_destroy(pcsf_model *m) {
     for (DevBuf *b : bufs) b->release();
     for (auto &e : m->ev) if (e) cudaEventDestroy(e);
     delete m;
+}
+
+extern "C" pcsf_status pcsf_score_msa_stats(const pcsf_model *m, pcsf_msa_stats *stats) {
+    if (!m || !stats) return fail(PCSF_ERR_INVALID, "pcsf_score_msa_stats: null argument");
+    const MleStats &s = m->msa_stats;
+    *stats = pcsf_msa_stats{s.alignments, s.evaluations, s.rounds, s.slots, s.ms_step, s.ms_plan, s.ms_expm, s.ms_prune};
+    return PCSF_OK;
 }
 
 extern "C" pcsf_status pcsf_model_get(const pcsf_model *m, int which, double *lambda, double *pi, double *P) {
@@ -753,7 +761,7 @@ extern "C" pcsf_status pcsf_score_msa(pcsf_model *m, pcsf_strategy strategy, int
         b.d_phylo = phylo ? d_phylo : nullptr;
         b.d_anc = anc ? d_anc : nullptr;
         if ((rc = mle_run(m->host, b, m->d_eig, m->d_bl, m->d_program, m->d_pi, m->d_logpi, m->mle, m->sm_count,
-                          m->prune_smem, m->prune_nwarp, st, g_err, &m->launches)))
+                          m->prune_smem, m->prune_nwarp, st, g_err, &m->launches, &m->msa_stats, m->timing)))
             return rc;
         // BLS for MLE uses the same per-alignment sum kernel with phylo/anc disabled
         if (bls) {

@@ -644,6 +644,65 @@ int main_dump_alignments(int argc, char **argv) {
     return 0;
 }
 
+// Test / bench tooling (no GPU needed): a raw [nl][ncols] ASCII matrix (the synthetic workload, phylocsfpp_b200/synth.py) as a MAF file
+// with the shape tools/make_synth_maf.py writes for its plain case — blocks of --block columns, a hole of 1..300 bases after every
+// --chain columns, species whose cells are all N in a block left out — fast enough for files of 10^8 columns.
+int main_matrix_to_maf(int argc, char **argv) {
+    const Args a = parse_args(argc, argv, {"block", "chain", "start"});
+    if (a.pos.size() != 4) die("usage: phylocsf_b200 matrix-to-maf [--block INT] [--chain INT] [--start INT] <model> <matrix.bin> <ncols> <out.maf>");
+    Model model;
+    load_model(model, a.pos[0], "", "");
+    const int nl = model.nl();
+    const int64_t ncols = atoll(a.pos[2].c_str()), block = std::max(1, a.integer("block", 120));
+    const int64_t chain = a.has("chain") ? atoll(a.str("chain").c_str()) : 0, start0 = a.has("start") ? atoll(a.str("start").c_str()) : 10000;
+    FILE *fi = fopen(a.pos[1].c_str(), "rb");
+    if (!fi) die("cannot open %s", a.pos[1].c_str());
+    std::vector<uint8_t> mat((size_t)nl * ncols);
+    if (fread(mat.data(), 1, mat.size(), fi) != mat.size()) die("%s is shorter than %d x %" PRId64 " bytes", a.pos[1].c_str(), nl, ncols);
+    fclose(fi);
+    std::vector<std::string> names(nl);
+    for (int s = 0; s < nl; ++s) {
+        const std::string &label = model.tree.labels[s];
+        auto it = model.aliases.find(label);
+        names[s] = (it != model.aliases.end() && !it->second.empty()) ? it->second[0] : label;
+    }
+    FILE *fo = fopen(a.pos[3].c_str(), "wb");
+    if (!fo) die("cannot create %s", a.pos[3].c_str());
+    std::vector<char> buf((size_t)16 << 20);
+    setvbuf(fo, buf.data(), _IOFBF, buf.size());
+    fputs("##maf version=1 scoring=synthetic\n", fo);
+    const int64_t src_size = start0 + ncols + ncols / 100 + 400000 + (chain ? (ncols / chain + 1) * 301 : 0);
+    int64_t pos = start0, blocks = 0;
+    uint64_t lcg = 0x9E3779B97F4A7C15ull;
+    for (int64_t c0 = 0; c0 < ncols;) {
+        int64_t c1 = std::min(ncols, c0 + block);
+        if (chain && c0 / chain != (c1 - 1) / chain) c1 = (c0 / chain + 1) * chain;          // blocks do not straddle a chain boundary
+        const int64_t size = c1 - c0;
+        fputs("a score=0.0\n", fo);
+        for (int s = 0; s < nl; ++s) {
+            const uint8_t *row = mat.data() + (size_t)s * ncols + c0;
+            if (s == 0) {
+                fprintf(fo, "s %s.chr1 %" PRId64 " %" PRId64 " + %" PRId64 " ", names[0].c_str(), pos, size, src_size);
+            } else {
+                int64_t nb = 0, nn = 0;
+                for (int64_t i = 0; i < size; ++i) { nb += row[i] != '-'; nn += row[i] == 'N'; }
+                if (nn == size) continue;
+                fprintf(fo, "s %s.scaffold_%d %" PRId64 " %" PRId64 " %c 50000000 ", names[s].c_str(), s, 1000 + c0, nb, "+-"[s % 2]);
+            }
+            fwrite(row, 1, (size_t)size, fo);
+            fputc('\n', fo);
+        }
+        fputc('\n', fo);
+        pos += size;
+        ++blocks;
+        if (chain && c1 % chain == 0 && c1 < ncols) { lcg = lcg * 6364136223846793005ull + 1442695040888963407ull; pos += 1 + (int64_t)((lcg >> 33) % 300); }
+        c0 = c1;
+    }
+    fclose(fo);
+    printf("{\"columns\": %" PRId64 ", \"blocks\": %" PRId64 "}\n", ncols, blocks);
+    return 0;
+}
+
 // Test hook (no GPU needed): the PhyloCSF-HMM stage alone on existing raw tracks.
 int main_smooth_tracks(int argc, char **argv) {
     const Args a = parse_args(argc, argv, {"genome-length", "coding-exons", "output-phylo", "output-regions", "print-hmm"});
@@ -714,5 +773,6 @@ int main(int argc, char **argv) {
     if (tool == "score-msa") return main_score_msa(argc, argv);
     if (tool == "dump-alignments") return main_dump_alignments(argc, argv);
     if (tool == "format-selftest") return main_format_selftest(argc, argv);
+    if (tool == "matrix-to-maf") return main_matrix_to_maf(argc, argv);
     die("unknown tool '%s' (build-tracks and score-msa are available)", tool.c_str());
 }

@@ -44,3 +44,51 @@ def gather_ordered(obj, dst: int = 0):
     out = [None] * world if rank == dst else None
     dist.gather_object(obj, out, dst=dst)
     return out
+
+
+def column_ranges(total: int, parts: int, align: int = 1) -> List[Tuple[int, int]]:
+    """[lo, hi) column range of every rank for a strong-scaled run over `total` columns (boundaries on multiples of `align`)."""
+    cuts = [min(total, (total * p // parts + align - 1) // align * align) for p in range(parts)] + [total]
+    return [(cuts[p], max(cuts[p], cuts[p + 1])) for p in range(parts)]
+
+
+class OrderedHostBuffer:
+    """The host-side ordered gather of a one-node multi-process run without any collective: one [rows, total] array backed by a
+    file that every rank maps (tmpfs when it has the room), each rank writing the columns of its own range.  When the ranks are
+    done, rank 0 holds the merged tracks in column order — the analogue of the reference's merge of per-job files in job order
+    (src/phylocsf++build_tracks.hpp:27-53, 245-259).  `path` must be the same on every rank (e.g. derived from MASTER_PORT)."""
+
+    def __init__(self, path: str, rows: int, total: int, dtype="float64", create: bool = False):
+        import numpy as np
+        self.path, self.rows, self.total = path, rows, total
+        self.dtype = np.dtype(dtype)
+        nbytes = rows * total * self.dtype.itemsize
+        if create:
+            with open(path, "wb") as fh:
+                fh.truncate(nbytes)
+        self.arr = np.memmap(path, dtype=self.dtype, mode="r+", shape=(rows, total))
+
+    @staticmethod
+    def pick_dir(nbytes: int) -> str:
+        """tmpfs if it has room for nbytes (+10 %), else the system temporary directory."""
+        import os
+        import shutil
+        import tempfile
+        try:
+            if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > nbytes * 1.1:
+                return "/dev/shm"
+        except OSError:
+            pass
+        return tempfile.gettempdir()
+
+    def write(self, row: int, col0: int, values) -> None:
+        self.arr[row, col0:col0 + len(values)] = values
+
+    def close(self, unlink: bool = False) -> None:
+        import os
+        del self.arr
+        if unlink:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass

@@ -7,7 +7,7 @@ import numpy as np
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from phylocsfpp_b200.shard import contiguous_partition, gather_ordered
+from phylocsfpp_b200.shard import OrderedHostBuffer, column_ranges, contiguous_partition, gather_ordered
 
 
 def test_contiguous_partition_properties():
@@ -53,3 +53,34 @@ def test_two_rank_ordered_gather_matches_single_process():
         ret = mgr.dict()
         mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
         assert ret.get("ok") is True
+
+
+def _worker_shared(rank, world, port, path, total):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    if rank == 0:
+        OrderedHostBuffer(path, 2, total, create=True).close()
+    dist.barrier()
+    buf = OrderedHostBuffer(path, 2, total)
+    lo, hi = column_ranges(total, world, align=16)[rank]
+    for c0 in range(lo, hi, 1000):          # batches, as bench.py's config-4 leg writes them
+        c1 = min(hi, c0 + 1000)
+        buf.write(0, c0, np.arange(c0, c1, dtype=np.float64))
+        buf.write(1, c0, -np.arange(c0, c1, dtype=np.float64))
+    buf.arr.flush()
+    dist.barrier()
+    buf.close()
+    dist.destroy_process_group()
+
+
+def test_column_ranges_and_ordered_host_buffer(tmp_path):
+    """Strong-scaled column ranges + the file-backed ordered output: two ranks write their ranges, the merged array is the
+    single-process array (no collective on the data path)."""
+    for total, parts, align in ((1000, 3, 16), (250_000_000, 8, 1 << 22), (10, 4, 16), (0, 2, 1)):
+        r = column_ranges(total, parts, align)
+        assert r[0][0] == 0 and r[-1][1] == total and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        assert all(lo % align == 0 or lo == total for lo, _ in r)
+    total, path = 12345, os.path.join(str(tmp_path), "ordered.bin")
+    mp.spawn(_worker_shared, args=(2, _free_port(), path, total), nprocs=2, join=True)
+    merged = np.memmap(path, dtype=np.float64, mode="r", shape=(2, total))
+    assert np.array_equal(merged[0], np.arange(total)) and np.array_equal(merged[1], -np.arange(total, dtype=np.float64))

@@ -15,6 +15,7 @@
 #include <condition_variable>
 #include <cmath>
 
+#include "annotate.hpp"
 #include "hmm.hpp"
 #include "maf.hpp"
 
@@ -158,7 +159,7 @@ int print_model_info(const std::string &model_name) {
 // ------------------------------------------------------------------------------------------- build-tracks
 int main_build_tracks(int argc, char **argv) {
     const Args a = parse_args(argc, argv, {"output-raw-phylo", "output-phylo", "output-regions", "power-threshold", "genome-length", "coding-exons",
-                                           "threads", "output", "mapping", "species", "gpus", "precision", "model-info"});
+                                           "threads", "output", "mapping", "species", "gpus", "precision", "model-info", "output-bigwig"});
     if (a.has("model-info")) return print_model_info(a.str("model-info"));          // build_tracks.hpp:401-405
     if (a.pos.size() < 2) die("usage: phylocsf_b200 build-tracks [OPTIONS] <model> <alignments>...");
     const bool keep_raw = a.boolean("output-raw-phylo", true);
@@ -169,6 +170,9 @@ int main_build_tracks(int argc, char **argv) {
         return -1;
     }
     const bool raw = keep_raw || smooth || regions;          // the raw tracks are the HMM's input (build_tracks.hpp:109,248)
+    // --output-bigwig 1: every wig file written is also indexed as <name>.bw (the reference leaves that to UCSC's wigToBigWig); the
+    // chromosome lengths are the srcSize fields of the reference rows
+    const bool to_bigwig = a.boolean("output-bigwig", false);
     Hmm hmm_model{};
     if (smooth || regions)          // models.hpp:1760-1764 (the reference estimates only for --output-phylo and leaves the HMM unset for regions alone)
         hmm_model = coding_hmm(estimate_hmm_params(a.str("coding-exons"), (uint32_t)strtoull(a.str("genome-length").c_str(), nullptr, 10)));
@@ -422,6 +426,24 @@ int main_build_tracks(int argc, char **argv) {
     }
     for (auto &w : workers) w.join();
     total_cols += cols;
+    if (to_bigwig) {
+        std::map<std::string, std::map<std::string, uint32_t>> sizes;          // output directory -> chromosome -> length
+        for (const FileCtx &fc : fctx)
+            for (const MafFile::Chain &c : fc.maf->chains())
+                if (c.ref_id >= 0) { uint32_t &l = sizes[fc.out_dir][c.chrom]; l = std::max<uint32_t>(l, (uint32_t)c.chrom_len); }
+        std::vector<std::thread> conv;
+        for (const auto &dir : sizes) {
+            const std::vector<std::pair<std::string, uint32_t>> chroms(dir.second.begin(), dir.second.end());
+            std::vector<std::string> names = {"PhyloCSFpower"};
+            for (int k = 0; k < 6; ++k) {
+                if (keep_raw) names.push_back(std::string("PhyloCSFRaw") + kFrames[k]);
+                if (smooth) names.push_back(std::string("PhyloCSF") + kFrames[k]);
+            }
+            for (const std::string &n : names)
+                conv.emplace_back([=] { wig_to_bigwig(dir.first + "/" + n + ".wig", chroms, dir.first + "/" + n + ".bw"); });
+        }
+        for (auto &t : conv) t.join();
+    }
     const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
     printf("\nDone!\n");
     if (getenv("PCSF_HOST_STATS")) {
@@ -703,6 +725,51 @@ int main_matrix_to_maf(int argc, char **argv) {
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------- track consumers
+// annotate-with-tracks (reference src/phylocsf++annotate_with_tracks.hpp:220-305): same positionals and --output.
+int main_annotate_with_tracks(int argc, char **argv) {
+    const Args a = parse_args(argc, argv, {"output"});
+    if (a.pos.size() < 2) die("usage: phylocsf_b200 annotate-with-tracks [--output DIR] <PhyloCSF+1.bw> <gff/gtf files>...");
+    const std::string out_dir = a.str("output");
+    if (!out_dir.empty() && create_directory(out_dir)) printf("Created the output directory.\n");
+    TrackSet tracks;
+    if (!open_tracks(a.pos[0], tracks)) return -1;
+    std::set<std::string> missing;
+    const std::string header = "# PhyloCSF scores computed with phylocsf_b200 (PhyloCSF++ compatible) and precomputed tracks " + a.pos[0] + "\n";
+    for (size_t i = 1; i < a.pos.size(); ++i) annotate_file(a.pos[i], out_dir, tracks, missing, header);
+    printf("\33[2K\rDone!\n");
+    return 0;
+}
+
+// wig-to-bigwig: the step the reference leaves to UCSC's wigToBigWig (README: "wigToBigWig PhyloCSF+1.wig chrom.sizes PhyloCSF+1.bw").
+int main_wig_to_bigwig(int argc, char **argv) {
+    const Args a = parse_args(argc, argv, {"compress"});
+    if (a.pos.size() != 3) die("usage: phylocsf_b200 wig-to-bigwig [--compress BOOL] <in.wig> <chrom.sizes> <out.bw>");
+    wig_to_bigwig(a.pos[0], read_chrom_sizes(a.pos[1]), a.pos[2], a.boolean("compress", true));
+    return 0;
+}
+
+// bigwig-dump: header facts + every interval as bedGraph lines (the text bigWigToBedGraph prints) — what the tests compare.
+int main_bigwig_dump(int argc, char **argv) {
+    const Args a = parse_args(argc, argv, {"intervals"});
+    if (a.pos.size() != 1) die("usage: phylocsf_b200 bigwig-dump [--intervals BOOL] <in.bw>");
+    BigWigReader r;
+    std::string err;
+    if (!r.open(a.pos[0], err)) die("%s", err.c_str());
+    const BigWigReader::Summary s = r.summary();
+    printf("# version %d zoom_levels %d sections %" PRIu64 " bases_covered %" PRIu64 " min %.6g max %.6g sum %.9g sum_squares %.9g\n", r.version(), r.zoom_levels(),
+           r.n_sections(), s.bases_covered, s.min, s.max, s.sum, s.sum_squares);
+    for (const auto &c : r.chroms()) printf("# chrom %s id %u length %u\n", c.name.c_str(), c.id, c.len);
+    if (a.boolean("intervals", true)) {
+        std::vector<std::string> names(r.chroms().size());
+        for (const auto &c : r.chroms()) if (c.id < names.size()) names[c.id] = c.name;
+        if (!r.for_each_interval([&](uint32_t chrom, uint32_t b, uint32_t e, float v) { printf("%s\t%u\t%u\t%.9g\n", chrom < names.size() ? names[chrom].c_str() : "?", b, e, v); }))
+            die("%s: damaged data section", a.pos[0].c_str());
+    }
+    return 0;
+}
+
 // Test hook (no GPU needed): the PhyloCSF-HMM stage alone on existing raw tracks.
 int main_smooth_tracks(int argc, char **argv) {
     const Args a = parse_args(argc, argv, {"genome-length", "coding-exons", "output-phylo", "output-regions", "print-hmm"});
@@ -762,9 +829,11 @@ int main(int argc, char **argv) {
         printf("phylocsf_b200 — B200-native PhyloCSF++ likelihood core behind the reference's command line\n\n"
                "  phylocsf_b200 build-tracks [--output-raw-phylo BOOL] [--output-phylo BOOL] [--output-regions BOOL] [--genome-length INT]\n"
                "                             [--coding-exons FILE] [--power-threshold FLOAT] [--threads INT] [--gpus INT]\n"
-               "                             [--precision f64|tc5] [--output DIR] [--mapping FILE] [--species LIST] <model> <maf>...\n"
+               "                             [--precision f64|tc5] [--output-bigwig BOOL] [--output DIR] [--mapping FILE] [--species LIST] <model> <maf>...\n"
                "  phylocsf_b200 score-msa    [--strategy MLE|FIXED|OMEGA|FIXED_MEAN] [--comp-phylo BOOL] [--comp-anc BOOL] [--threads INT] [--gpus INT]\n"
-               "                             [--output DIR] [--mapping FILE] [--species LIST] <model> <maf>...\n");
+               "                             [--output DIR] [--mapping FILE] [--species LIST] <model> <maf>...\n"
+               "  phylocsf_b200 annotate-with-tracks [--output DIR] <PhyloCSF+1.bw> <gff/gtf>...\n"
+               "  phylocsf_b200 wig-to-bigwig [--compress BOOL] <in.wig> <chrom.sizes> <out.bw>\n");
         return argc < 2 ? 1 : 0;
     }
     const std::string tool = argv[1];
@@ -774,5 +843,8 @@ int main(int argc, char **argv) {
     if (tool == "dump-alignments") return main_dump_alignments(argc, argv);
     if (tool == "format-selftest") return main_format_selftest(argc, argv);
     if (tool == "matrix-to-maf") return main_matrix_to_maf(argc, argv);
-    die("unknown tool '%s' (build-tracks and score-msa are available)", tool.c_str());
+    if (tool == "annotate-with-tracks") return main_annotate_with_tracks(argc, argv);
+    if (tool == "wig-to-bigwig") return main_wig_to_bigwig(argc, argv);
+    if (tool == "bigwig-dump") return main_bigwig_dump(argc, argv);
+    die("unknown tool '%s' (build-tracks, score-msa, annotate-with-tracks and wig-to-bigwig are available)", tool.c_str());
 }

@@ -19,3 +19,11 @@ gzip -9 -n -c "$REF/test/maf-file-medium/chr22.516alignments.maf" > "$HERE/score
 cp "$REF"/test/maf-file-medium/chr22.516alignments.maf.fixed.scores "$HERE/score-msa/"
 cp "$REF"/test/maf-file-medium/chr22.516alignments.maf.mle.scores "$HERE/score-msa/"
 chmod -R u+w "$HERE"
+# f-4: annotate-with-tracks (test/tests.sh:23-26): the example tracks, the three example annotations and the expected output
+mkdir -p "$HERE/annotate-with-tracks"
+cp "$REF"/example/tracks/PhyloCSF*.bw "$HERE/annotate-with-tracks/"
+for f in ensGene ncbiRefSeq refGene; do
+  gzip -9 -n -c "$REF/example/galGal6_chr22_25_28_subset_$f.gtf" > "$HERE/annotate-with-tracks/galGal6_chr22_25_28_subset_$f.gtf.gz"
+  gzip -9 -n -c "$REF/test/expected_results/annotate-with-tracks/galGal6_chr22_25_28_subset_$f.PhyloCSF++.gtf" > "$HERE/annotate-with-tracks/galGal6_chr22_25_28_subset_$f.PhyloCSF++.gtf.gz"
+done
+chmod -R u+w "$HERE"

@@ -158,6 +158,48 @@ def test_build_tracks_cli_smoothing(golden_dir, tmp_path):
 
 
 @pytest.mark.gpu
+def test_maf_to_bigwig_to_annotation(golden_dir, tmp_path):
+    """The whole chain without an external tool: build-tracks --output-phylo 1 --output-bigwig 1 (CUDA likelihoods -> wig text -> HMM ->
+    bigWig) -> annotate-with-tracks.  Checked against the same annotation computed from bigWigs made of the files the REFERENCE wrote
+    for this input (smooth53 fixtures + its expected PhyloCSFpower.wig): identical text, and the .bw files hold exactly the wig values."""
+    _need_bin()
+    from tests.test_host_annotate import CHROMS, SETS, _body, _sizes_file, parse_bigwig, wig_intervals
+    G = os.path.join(golden_dir, "build-tracks")
+    A = os.path.join(golden_dir, "annotate-with-tracks")
+    tmp = str(tmp_path)
+    maf = _gunzip(os.path.join(G, "galGal6_chr22_25_28_each_30k_bases.maf.gz"), tmp)
+    _, exons, glen = _smooth_inputs(golden_dir, tmp_path, "smooth53")
+    out = os.path.join(tmp, "out_bw")
+    subprocess.run([BIN, "build-tracks", "--threads", "4", "--output-phylo", "1", "--output-bigwig", "1", "--genome-length", glen, "--coding-exons", exons,
+                    "--output", out, os.path.join(G, "53birds"), maf], check=True, capture_output=True)
+    for name in ["PhyloCSFpower"] + [f"PhyloCSF{k}" for k in FRAMES6] + [f"PhyloCSFRaw{k}" for k in FRAMES6]:
+        bw = parse_bigwig(os.path.join(out, name + ".bw"))
+        assert {v[0]: v[1] for v in bw["chroms"].values()} == CHROMS          # lengths taken from the MAF's srcSize fields
+        assert bw["intervals"] == sorted(wig_intervals(os.path.join(out, name + ".wig"))), name
+    # the same tracks made of the reference-written wig files
+    refdir = os.path.join(tmp, "ref_bw")
+    os.makedirs(refdir)
+    sizes = _sizes_file(tmp)
+    wigs = {"PhyloCSFpower": os.path.join(G, "PhyloCSFpower.wig.gz")}
+    wigs.update({f"PhyloCSF{k}": os.path.join(golden_dir, "ref-generated", f"smooth53.PhyloCSF{k}.wig.gz") for k in FRAMES6})
+    for name, gz in wigs.items():
+        wig = os.path.join(refdir, name + ".wig")
+        with gzip.open(gz, "rb") as fi, open(wig, "wb") as fo:
+            shutil.copyfileobj(fi, fo)
+        subprocess.run([BIN, "wig-to-bigwig", wig, sizes, os.path.join(refdir, name + ".bw")], check=True, capture_output=True)
+    gtfs = [_gunzip(os.path.join(A, f"galGal6_chr22_25_28_subset_{n}.gtf.gz"), tmp) for n in SETS]
+    for d, tracks in (("ann_gpu", out), ("ann_ref", refdir)):
+        subprocess.run([BIN, "annotate-with-tracks", "--output", os.path.join(tmp, d), os.path.join(tracks, "PhyloCSF+1.bw")] + gtfs, check=True, capture_output=True)
+    n_scored = 0
+    for n in SETS:
+        a = _body(os.path.join(tmp, "ann_gpu", f"galGal6_chr22_25_28_subset_{n}.PhyloCSF++.gtf"))
+        b = _body(os.path.join(tmp, "ann_ref", f"galGal6_chr22_25_28_subset_{n}.PhyloCSF++.gtf"))
+        assert a == b, n
+        n_scored += sum("phylocsf_score_weighted_mean=" in ln and "mean=nan" not in ln for ln in a)
+    assert n_scored > 100
+
+
+@pytest.mark.gpu
 def test_build_tracks_cli_golden(golden_dir, tmp_path):
     """Config 1 through the command line tool: the reference's seven expected wig files, byte for byte (FP64 path), with
     one and with several threads; the tcgen05 path within 1e-3 decibans of them."""

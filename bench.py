@@ -374,9 +374,10 @@ def leg_config5(total_aln, rank, world, local_rank, dist, torch, capi):
     return out
 
 
-def leg_cli(cols, rank, world, local_rank, torch):
-    """The drop-in command line on a config-3 shaped MAF file in tmpfs: phylocsf_b200 build-tracks --gpus N --precision tc5, MAF text
-    -> 7 wig files.  Rank 0 runs the process (it deals chain groups to all N devices itself); the other ranks keep their GPUs idle."""
+def leg_cli(cols, rank, world, local_rank, torch, n_files=4):
+    """The drop-in command line at BASELINE config 3's size: phylocsf_b200 build-tracks --gpus N --precision tc5 on `n_files` chromosome
+    MAF files in tmpfs (58mammals, cols / n_files columns each), MAF text -> 7 wig files.  Rank 0 runs the process (it deals chain
+    groups to all N devices itself); the other ranks keep their GPUs idle."""
     import shutil
     import tempfile
     from phylocsfpp_b200.models import load_model
@@ -385,40 +386,57 @@ def leg_cli(cols, rank, world, local_rank, torch):
     if rank == 0:
         BIN = os.path.join(ROOT, "phylocsfpp_b200", "bin", "phylocsf_b200")
         model = load_model("58mammals")
-        base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > 3 * 58 * cols else None
+        base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > 4 * 58 * cols else None
         tmp = tempfile.mkdtemp(prefix="pcsf_cli_", dir=base)
         try:
             dev = torch.device("cuda", local_rank)
+            per = cols // n_files
             piece = 1 << 23
-            with open(os.path.join(tmp, "m.bin"), "wb") as fh:
-                rows = []
-                for c0 in range(0, cols, piece):
-                    n = min(piece, cols - c0)
-                    rows.append(synth_alignment(model, n, seed=5000 + c0 // piece, device=dev)[:, :n].cpu().numpy())
-                np.concatenate(rows, axis=1).tofile(fh)
-            del rows
+            t_gen = time.perf_counter()
+            procs, mafs = [], []
+            for f in range(n_files):
+                mbin = os.path.join(tmp, f"m{f}.bin")
+                # [nl][per] row-major, written piece by piece through a memmap (the pieces are column ranges)
+                mm = np.lib.format.open_memmap(mbin + ".npy", mode="w+", dtype=np.uint8, shape=(model.nl, per))
+                for c0 in range(0, per, piece):
+                    n = min(piece, per - c0)
+                    mm[:, c0:c0 + n] = synth_alignment(model, n, seed=5000 + 100 * f + c0 // piece, device=dev)[:, :n].cpu().numpy()
+                off = mm.offset
+                del mm
+                maf = os.path.join(tmp, f"chr{f + 1}.maf")
+                mafs.append(maf)
+                procs.append(subprocess.Popen([BIN, "matrix-to-maf", "--chain", str(25_000_000), "--chrom", f"chr{f + 1}", "--skip-bytes", str(off), "58mammals",
+                                               mbin + ".npy", str(per), maf], stdout=subprocess.DEVNULL))
+            for pr in procs:
+                if pr.wait() != 0:
+                    raise SystemExit("matrix-to-maf failed")
+            for f in range(n_files):
+                os.unlink(os.path.join(tmp, f"m{f}.bin.npy"))
             torch.cuda.empty_cache()
-            maf = os.path.join(tmp, "cfg3.maf")
-            subprocess.run([BIN, "matrix-to-maf", "--chain", str(25_000_000), "58mammals", os.path.join(tmp, "m.bin"), str(cols), maf],
-                           check=True, capture_output=True)
-            os.unlink(os.path.join(tmp, "m.bin"))
+            t_gen = time.perf_counter() - t_gen
             threads = os.cpu_count() or 1
             best = None
             for rep in range(2):
                 t0 = time.perf_counter()
                 r = subprocess.run([BIN, "build-tracks", "--threads", str(threads), "--gpus", str(world), "--precision", "tc5", "--output",
-                                    os.path.join(tmp, "out"), "58mammals", maf], check=True, capture_output=True, text=True,
+                                    os.path.join(tmp, "out")] + ["58mammals"] + mafs, check=True, capture_output=True, text=True,
                                    env=dict(os.environ, PCSF_HOST_STATS="1"))
                 dt = time.perf_counter() - t0
-                st = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][0])
-                if best is None or st["seconds"] < best[1]["seconds"]:
+                js = [json.loads(ln) for ln in r.stdout.splitlines() if ln.startswith("{")]
+                st = js[0]
+                for extra in js[1:]:
+                    st.update(extra)
+                if best is None or dt < best[0]:
                     best = (dt, st)
             wig_bytes = sum(os.path.getsize(os.path.join(tmp, "out", f)) for f in os.listdir(os.path.join(tmp, "out")))
-            out = {"workload": f"phylocsf_b200 build-tracks --gpus {world} --precision tc5 --threads {threads} on a synthetic 58mammals MAF file "
-                               f"({cols} columns, {os.path.getsize(maf)} bytes, tmpfs) -> PhyloCSFpower.wig + 6 PhyloCSFRaw wigs ({wig_bytes} bytes)",
-                   "columns": cols, "tool_seconds": best[1]["seconds"], "columns_per_s": cols / best[1]["seconds"],
-                   "process_seconds": best[0], "columns_per_s_process": cols / best[0], "n_gpus": world, "host_threads": threads,
-                   "tool_stats": best[1], "note": "tool_seconds = models ready -> files written; process_seconds adds CUDA context + model preparation"}
+            maf_bytes = sum(os.path.getsize(m) for m in mafs)
+            ncols = per * n_files
+            out = {"workload": f"phylocsf_b200 build-tracks --gpus {world} --precision tc5 --threads {threads} on {n_files} synthetic 58mammals chromosome MAF files "
+                               f"({ncols} columns, {maf_bytes} bytes, tmpfs; blocks of 120 columns, 30% missing cells) -> PhyloCSFpower.wig + 6 PhyloCSFRaw wigs ({wig_bytes} bytes)",
+                   "columns": ncols, "process_seconds": best[0], "columns_per_s": ncols / best[0], "tool_seconds": best[1]["seconds"],
+                   "columns_per_s_tool": ncols / best[1]["seconds"], "n_gpus": world, "host_threads": threads,
+                   "tool_stats": best[1], "generate_seconds": t_gen,
+                   "note": "process_seconds = the whole command (exec -> exit: CUDA context, model preparation, scan, scoring, 7 files written); tool_seconds = inside main after option parsing; best of 2 runs"}
         finally:
             shutil.rmtree(tmp, ignore_errors=True)
     _file_barrier("cli", rank, world)
@@ -440,7 +458,7 @@ def main():
     ap.add_argument("--no-dedup", action="store_true")
     ap.add_argument("--config4-cols", type=int, default=250_000_000, help="columns of the strong-scaled 100vertebrates leg (0 = skip)")
     ap.add_argument("--config5-alignments", type=int, default=1_000_000, help="alignments of the strong-scaled MLE leg (0 = skip)")
-    ap.add_argument("--cli-cols", type=int, default=1 << 24, help="columns of the MAF file of the command-line leg (0 = skip)")
+    ap.add_argument("--cli-cols", type=int, default=100_000_000, help="columns of the MAF files of the command-line leg, four chromosome files (0 = skip)")
     ap.add_argument("--precision", default="tc5", choices=["f64", "tc5"],
                     help="tc5: tcgen05/TMEM split-TF32 path (fastest path inside the 1e-3 deciban contract); "
                          "f64: FP64 DMMA path (parity anchor, byte-identical wig text)")

@@ -646,6 +646,16 @@ extern "C" void *pcsf_alloc_pinned(size_t bytes) {
     return p;
 }
 extern "C" void pcsf_free_pinned(void *p) { if (p) cudaFreeHost(p); }
+extern "C" pcsf_status pcsf_register_host(void *p, size_t bytes) {
+    if (!p || !bytes) return fail(PCSF_ERR_INVALID, "pcsf_register_host: null argument");
+    if (cudaHostRegister(p, bytes, cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); return fail(PCSF_ERR_CUDA, "cudaHostRegister failed"); }
+    return PCSF_OK;
+}
+extern "C" pcsf_status pcsf_unregister_host(void *p) {
+    if (!p) return PCSF_OK;
+    if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return fail(PCSF_ERR_CUDA, "cudaHostUnregister failed"); }
+    return PCSF_OK;
+}
 extern "C" int pcsf_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }

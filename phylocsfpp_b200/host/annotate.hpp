@@ -259,7 +259,8 @@ inline void wig_to_bigwig(const std::string &wig_path, const std::vector<std::pa
             Run r{"", 0, 0, 1, 1, le + 1, size};
             unsigned long long start1 = 0;
             std::string line(mem + p, le - p);
-            for (char *tok = strtok(&line[0], " \t\r"); tok; tok = strtok(nullptr, " \t\r")) {
+            char *save = nullptr;          // strtok_r: build-tracks converts its wig files on parallel threads
+            for (char *tok = strtok_r(&line[0], " \t\r", &save); tok; tok = strtok_r(nullptr, " \t\r", &save)) {
                 if (!strncmp(tok, "chrom=", 6)) r.chrom = tok + 6;
                 else if (!strncmp(tok, "start=", 6)) start1 = strtoull(tok + 6, nullptr, 10);
                 else if (!strncmp(tok, "step=", 5)) r.step = (uint32_t)strtoul(tok + 5, nullptr, 10);

@@ -106,15 +106,18 @@ struct ModelPool {
 struct PinnedBuf {
     void *p = nullptr;
     size_t cap = 0;
+    double alloc_seconds = 0.0;
     PinnedBuf() = default;
     PinnedBuf(const PinnedBuf &) = delete;
     ~PinnedBuf() { pcsf_free_pinned(p); }
     template <class T> T *get(size_t n) {
         const size_t bytes = n * sizeof(T);
         if (bytes > cap) {
+            const auto t0 = std::chrono::steady_clock::now();
             pcsf_free_pinned(p);
             cap = bytes + bytes / 4 + 4096;
             p = pcsf_alloc_pinned(cap);
+            alloc_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
             if (!p) die("cannot allocate %zu bytes of page-locked memory: %s", cap, pcsf_last_error());
         }
         return reinterpret_cast<T *>(p);
@@ -158,6 +161,7 @@ int print_model_info(const std::string &model_name) {
 
 // ------------------------------------------------------------------------------------------- build-tracks
 int main_build_tracks(int argc, char **argv) {
+    const auto t_entry = std::chrono::steady_clock::now();
     const Args a = parse_args(argc, argv, {"output-raw-phylo", "output-phylo", "output-regions", "power-threshold", "genome-length", "coding-exons",
                                            "threads", "output", "mapping", "species", "gpus", "precision", "model-info", "output-bigwig"});
     if (a.has("model-info")) return print_model_info(a.str("model-info"));          // build_tracks.hpp:401-405
@@ -185,18 +189,20 @@ int main_build_tracks(int argc, char **argv) {
     Model model;
     load_model(model, a.pos[0], a.str("species"), a.str("mapping"));
     const int nl = model.nl();
+    // Start-up overlaps three things: the device models (CUDA context + eigensystems + uploads, two per GPU) are prepared by their own
+    // threads while the input files are scanned and cut into chains, and while the page-locked staging slab is allocated.
+    const auto t_start = std::chrono::steady_clock::now();
     std::vector<std::unique_ptr<ModelPool>> pools;
-    make_pools(model, gpus, 2, pools);
+    const int per_gpu = getenv("PCSF_HOST_MODELS_PER_GPU") ? std::max(1, atoi(getenv("PCSF_HOST_MODELS_PER_GPU"))) : 2;
+    std::thread pool_maker([&] { make_pools(model, gpus, per_gpu, pools); });
     std::vector<std::vector<uint8_t>> seen(threads, std::vector<uint8_t>(nl, 0));
-    double t_parse = 0.0, t_format = 0.0, t_scan = 0.0;
+    double t_parse = 0.0, t_format = 0.0, t_scan = 0.0, t_wait_model = 0.0, t_wait_writer = 0.0;
     const bool dev_timing = getenv("PCSF_HOST_TIMING") != nullptr;          // per-stage CUDA-event times of every library call (diagnostic)
-    if (dev_timing) for (auto &p : pools) for (pcsf_model *dm : p->all) pcsf_set_timing(dm, 1);
     double dev_ms[6] = {0, 0, 0, 0, 0, 0};
     int64_t dev_unique = 0, dev_windows = 0;
     static const char *kFrames[6] = {"+1", "+2", "+3", "-1", "-2", "-3"};
     int64_t total_cols = 0;
     double t_gpu = 0.0;
-    const auto t_start = std::chrono::steady_clock::now();
 
     // All input files are scanned first and their chain groups go into ONE work queue: the workers never wait at a file boundary
     // (chromosome-sized files used to end with a partially filled round of workers each); the writer still emits file after file.
@@ -238,6 +244,45 @@ int main_build_tracks(int argc, char **argv) {
         total_chains += chains.size();
         fctx.push_back(std::move(fc));
     }
+    // Staging, one region per worker, sized by the largest group (known exactly from the scan).  Pinning runs at 1-2 GB/s and competes
+    // with the model preparation for the driver, so the regions are plain page-aligned memory that the workers parse into from the
+    // first millisecond; once the models are up a background thread page-locks them in place, one after the other
+    // (pcsf_register_host).  Calls made before a region is pinned are simply staged by the driver.
+    int64_t max_group_cols = 1;
+    for (const Group &g : groups) {
+        int64_t n = 0;
+        const std::vector<MafFile::Chain> &chains = fctx[g.file].maf->chains();
+        for (size_t ci = g.c0; ci < g.c1; ++ci) n += chains[ci].ref_id < 0 ? 0 : chains[ci].ref_cols;
+        max_group_cols = std::max(max_group_cols, n);
+    }
+    const size_t mat_bytes = ((size_t)nl * max_group_cols + 4095) / 4096 * 4096, vec_bytes = ((size_t)max_group_cols * 8 + 4095) / 4096 * 4096;
+    const size_t per_thread = mat_bytes + 3 * vec_bytes;
+    const int slab_threads = (int)std::min<size_t>((size_t)threads, std::max<size_t>(groups.size(), 1));
+    std::vector<uint8_t *> slabs(slab_threads, nullptr);
+    for (auto &p : slabs)
+        if (posix_memalign(reinterpret_cast<void **>(&p), 4096, per_thread) != 0) die("cannot allocate %zu bytes of staging memory", per_thread);
+    std::mutex ready_mu;
+    std::condition_variable ready_cv;
+    bool pools_ready = false;
+    std::atomic<bool> stop_pinning{false};
+    std::vector<char> pinned(slab_threads, 0);
+    double t_slab = 0.0, t_startup = 0.0;
+    std::thread pool_waiter([&] {
+        pool_maker.join();
+        if (dev_timing) for (auto &p : pools) for (pcsf_model *dm : p->all) pcsf_set_timing(dm, 1);
+        if (getenv("PCSF_HOST_CHUNK_COLS")) for (auto &p : pools) for (pcsf_model *dm : p->all) pcsf_set_chunk_columns(dm, atoll(getenv("PCSF_HOST_CHUNK_COLS")));
+        t_startup = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+        { std::lock_guard<std::mutex> g(ready_mu); pools_ready = true; }
+        ready_cv.notify_all();
+        // Pinning pays only on long runs: ~1 s per GB during which the library calls of the other threads crawl (measured: 100 M
+        // columns take 1.9 s unpinned, 2.5-3.0 s with any pinning scheme), against 0.4 s saved per 100 M columns once pinned.
+        const char *pin_env = getenv("PCSF_HOST_PINNING");
+        const bool pin = pin_env ? atoi(pin_env) != 0 : cols_before >= (int64_t)400000000;
+        if (!pin) return;
+        const auto a0 = std::chrono::steady_clock::now();
+        for (int t = 0; t < slab_threads && !stop_pinning; ++t) pinned[t] = pcsf_register_host(slabs[t], per_thread) == PCSF_OK;
+        t_slab = std::chrono::duration<double>(std::chrono::steady_clock::now() - a0).count();
+    });
     OrderedSink sink;
     sink.resize(total_chains);
     std::atomic<size_t> next{0};
@@ -254,20 +299,26 @@ int main_build_tracks(int argc, char **argv) {
     std::vector<std::thread> workers;
     for (int t = 0; t < threads; ++t)
         workers.emplace_back([&, t] {
+                if (t >= slab_threads) return;          // fewer groups than threads
                 std::vector<Alignment> alns;
-                PinnedBuf mat_buf, plus_buf, minus_buf, bls_buf;
+                uint8_t *const my_slab = slabs[t];
+                bool have_pools = false;
+                std::vector<uint8_t> fallback_mat;          // only for a group whose text disagrees with its size fields
+                std::vector<double> fallback_out;
                 const uint8_t *src = nullptr;
                 double *plus = nullptr, *minus = nullptr, *bls = nullptr;
-                double my_gpu = 0.0, my_parse = 0.0, my_fmt = 0.0;
+                double my_gpu = 0.0, my_parse = 0.0, my_fmt = 0.0, my_wait_model = 0.0, my_wait_writer = 0.0;
                 auto now = [] { return std::chrono::steady_clock::now(); };
                 auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
                 for (size_t gi = next++; gi < groups.size(); gi = next++) {
                     const Group &grp = groups[gi];
+                    const auto w0 = now();
                     {
                         std::unique_lock<std::mutex> g(written_mu);
                         written_cv.wait(g, [&] { return grp.col_begin <= written_cols + AHEAD_COLS; });
                     }
                     const auto p0 = now();
+                    my_wait_writer += secs(w0, p0);
                     MafFile &maf = *fctx[grp.file].maf;
                     const std::vector<MafFile::Chain> &chains = maf.chains();
                     const size_t c0 = grp.c0, c1 = grp.c1, chain0 = fctx[grp.file].chain0;
@@ -278,7 +329,7 @@ int main_build_tracks(int argc, char **argv) {
                     int64_t Ltot = 0;
                     std::vector<int64_t> col0(c1 - c0);
                     for (size_t ci = c0; ci < c1; ++ci) { col0[ci - c0] = Ltot; Ltot += chains[ci].ref_id < 0 ? 0 : chains[ci].ref_cols; }
-                    uint8_t *mat = mat_buf.get<uint8_t>((size_t)nl * std::max<int64_t>(Ltot, 1));
+                    uint8_t *mat = my_slab;
                     bool direct = true;
                     for (size_t ci = c0; ci < c1 && direct; ++ci) {
                         const MafFile::Chain &c = chains[ci];
@@ -295,20 +346,35 @@ int main_build_tracks(int argc, char **argv) {
                             col0[ci - c0] = Ltot;
                             Ltot += alns[ci - c0].L;
                         }
-                        mat = mat_buf.get<uint8_t>((size_t)nl * std::max<int64_t>(Ltot, 1));
+                        if (Ltot > max_group_cols) {          // measured longer than announced: pageable staging for this one group
+                            fallback_mat.resize((size_t)nl * Ltot);
+                            mat = fallback_mat.data();
+                        }
                         for (size_t k = 0; k < c1 - c0; ++k)
                             for (int s = 0; s < nl; ++s)
                                 if (alns[k].L) memcpy(mat + (size_t)s * Ltot + col0[k], alns[k].seqs.data() + (size_t)s * alns[k].L, (size_t)alns[k].L);
                     }
                     if (Ltot > 0) {
                         src = mat;
-                        plus = plus_buf.get<double>((size_t)std::max<int64_t>(Ltot - 2, 1));
-                        minus = minus_buf.get<double>((size_t)std::max<int64_t>(Ltot - 2, 1));
-                        bls = bls_buf.get<double>((size_t)Ltot);
-                        my_parse += secs(p0, now());
+                        if (Ltot > max_group_cols) {
+                            fallback_out.resize((size_t)3 * Ltot);
+                            plus = fallback_out.data(); minus = plus + Ltot; bls = minus + Ltot;
+                        } else {
+                            plus = reinterpret_cast<double *>(my_slab + mat_bytes);
+                            minus = reinterpret_cast<double *>(my_slab + mat_bytes + vec_bytes);
+                            bls = reinterpret_cast<double *>(my_slab + mat_bytes + 2 * vec_bytes);
+                        }
+                        const auto p1 = now();
+                        my_parse += secs(p0, p1);
+                        if (!have_pools) {
+                            std::unique_lock<std::mutex> g(ready_mu);
+                            ready_cv.wait(g, [&] { return pools_ready; });
+                            have_pools = true;
+                        }
                         ModelPool &pool = *pools[gi % gpus];
                         pcsf_model *dm = pool.acquire();
                         const auto g0 = now();
+                        my_wait_model += secs(p1, g0);
                         pcsf_tracks_stats cs{};
                         const pcsf_status st = pcsf_tracks(dm, src, Ltot, Ltot, PCSF_TRACKS_BLS | (raw ? PCSF_TRACKS_SCORES : 0) | pflag,
                                                            plus, minus, bls, nullptr, &cs);
@@ -379,7 +445,8 @@ int main_build_tracks(int argc, char **argv) {
                     my_fmt += secs(f0, now());
                 }
                 std::lock_guard<std::mutex> g(gpu_time_mu);
-                t_gpu += my_gpu; t_parse += my_parse; t_format += my_fmt;
+                t_gpu += my_gpu; t_parse += my_parse; t_format += my_fmt; t_wait_model += my_wait_model; t_wait_writer += my_wait_writer;
+
         });
     for (size_t fi = 0; fi < fctx.size(); ++fi) {
         const std::string &out_dir = fctx[fi].out_dir;
@@ -425,6 +492,8 @@ int main_build_tracks(int argc, char **argv) {
         }
     }
     for (auto &w : workers) w.join();
+    stop_pinning = true;
+    pool_waiter.join();
     total_cols += cols;
     if (to_bigwig) {
         std::map<std::string, std::map<std::string, uint32_t>> sizes;          // output directory -> chromosome -> length
@@ -450,8 +519,9 @@ int main_build_tracks(int argc, char **argv) {
         std::string per_gpu;
         for (int g = 0; g < gpus; ++g) per_gpu += (g ? ", " : "") + std::to_string((long long)gpu_cols[g]);
         printf("{\"columns\": %" PRId64 ", \"seconds\": %.3f, \"columns_per_s\": %.1f, \"threads\": %d, \"gpus\": %d, \"scan_seconds\": %.3f, "
-               "\"parse_seconds_sum\": %.3f, \"gpu_call_seconds_sum\": %.3f, \"format_seconds_sum\": %.3f, \"columns_per_gpu\": [%s]}\n",
-               total_cols, wall, total_cols / wall, threads, gpus, t_scan, t_parse, t_gpu, t_format, per_gpu.c_str());
+               "\"startup_seconds\": %.3f, \"parse_seconds_sum\": %.3f, \"pinned_alloc_seconds\": %.3f, \"wait_model_seconds_sum\": %.3f, \"wait_writer_seconds_sum\": %.3f, "
+               "\"gpu_call_seconds_sum\": %.3f, \"format_seconds_sum\": %.3f, \"columns_per_gpu\": [%s]}\n",
+               total_cols, wall, total_cols / wall, threads, gpus, t_scan, t_startup, t_parse, t_slab, t_wait_model, t_wait_writer, t_gpu, t_format, per_gpu.c_str());
     }
     if (dev_timing)
         printf("{\"ms_pack\": %.2f, \"ms_hash\": %.2f, \"ms_dedup\": %.2f, \"ms_prune\": %.2f, \"ms_scatter\": %.2f, \"ms_bls\": %.2f, \"windows\": %" PRId64
@@ -462,7 +532,17 @@ int main_build_tracks(int argc, char **argv) {
         for (int t = 0; t < threads; ++t) any |= seen[t][s] != 0;
         if (!any) printf("\033[33mWARNING: species %s from the model was never seen in any alignment.\033[0m\n", model.tree.labels[s].c_str());
     }
+    const auto x0 = std::chrono::steady_clock::now();
+    for (int t = 0; t < slab_threads; ++t) { if (pinned[t]) pcsf_unregister_host(slabs[t]); free(slabs[t]); }
+    const auto x1 = std::chrono::steady_clock::now();
     for (auto &p : pools) p->destroy();
+    const auto x2 = std::chrono::steady_clock::now();
+    fctx.clear();
+    const auto x3 = std::chrono::steady_clock::now();
+    if (getenv("PCSF_HOST_STATS"))
+        printf("{\"teardown_buffers_seconds\": %.3f, \"teardown_models_seconds\": %.3f, \"teardown_files_seconds\": %.3f, \"before_start_seconds\": %.3f}\n",
+               std::chrono::duration<double>(x1 - x0).count(), std::chrono::duration<double>(x2 - x1).count(), std::chrono::duration<double>(x3 - x2).count(),
+               std::chrono::duration<double>(t_start - t_entry).count());
     return 0;
 }
 
@@ -670,8 +750,8 @@ int main_dump_alignments(int argc, char **argv) {
 // with the shape tools/make_synth_maf.py writes for its plain case — blocks of --block columns, a hole of 1..300 bases after every
 // --chain columns, species whose cells are all N in a block left out — fast enough for files of 10^8 columns.
 int main_matrix_to_maf(int argc, char **argv) {
-    const Args a = parse_args(argc, argv, {"block", "chain", "start"});
-    if (a.pos.size() != 4) die("usage: phylocsf_b200 matrix-to-maf [--block INT] [--chain INT] [--start INT] <model> <matrix.bin> <ncols> <out.maf>");
+    const Args a = parse_args(argc, argv, {"block", "chain", "start", "chrom", "skip-bytes"});
+    if (a.pos.size() != 4) die("usage: phylocsf_b200 matrix-to-maf [--block INT] [--chain INT] [--start INT] [--chrom NAME] [--skip-bytes INT] <model> <matrix.bin> <ncols> <out.maf>");
     Model model;
     load_model(model, a.pos[0], "", "");
     const int nl = model.nl();
@@ -679,6 +759,8 @@ int main_matrix_to_maf(int argc, char **argv) {
     const int64_t chain = a.has("chain") ? atoll(a.str("chain").c_str()) : 0, start0 = a.has("start") ? atoll(a.str("start").c_str()) : 10000;
     FILE *fi = fopen(a.pos[1].c_str(), "rb");
     if (!fi) die("cannot open %s", a.pos[1].c_str());
+    const std::string chrom = a.str("chrom", "chr1");
+    if (a.has("skip-bytes")) fseeko(fi, (off_t)atoll(a.str("skip-bytes").c_str()), SEEK_SET);          // e.g. the header of a .npy file
     std::vector<uint8_t> mat((size_t)nl * ncols);
     if (fread(mat.data(), 1, mat.size(), fi) != mat.size()) die("%s is shorter than %d x %" PRId64 " bytes", a.pos[1].c_str(), nl, ncols);
     fclose(fi);
@@ -704,7 +786,7 @@ int main_matrix_to_maf(int argc, char **argv) {
         for (int s = 0; s < nl; ++s) {
             const uint8_t *row = mat.data() + (size_t)s * ncols + c0;
             if (s == 0) {
-                fprintf(fo, "s %s.chr1 %" PRId64 " %" PRId64 " + %" PRId64 " ", names[0].c_str(), pos, size, src_size);
+                fprintf(fo, "s %s.%s %" PRId64 " %" PRId64 " + %" PRId64 " ", names[0].c_str(), chrom.c_str(), pos, size, src_size);
             } else {
                 int64_t nb = 0, nn = 0;
                 for (int64_t i = 0; i < size; ++i) { nb += row[i] != '-'; nn += row[i] == 'N'; }

@@ -170,8 +170,9 @@ def test_maf_to_bigwig_to_annotation(golden_dir, tmp_path):
     maf = _gunzip(os.path.join(G, "galGal6_chr22_25_28_each_30k_bases.maf.gz"), tmp)
     _, exons, glen = _smooth_inputs(golden_dir, tmp_path, "smooth53")
     out = os.path.join(tmp, "out_bw")
-    subprocess.run([BIN, "build-tracks", "--threads", "4", "--output-phylo", "1", "--output-bigwig", "1", "--genome-length", glen, "--coding-exons", exons,
-                    "--output", out, os.path.join(G, "53birds"), maf], check=True, capture_output=True)
+    r = subprocess.run([BIN, "build-tracks", "--threads", "4", "--output-phylo", "1", "--output-bigwig", "1", "--genome-length", glen, "--coding-exons", exons,
+                        "--output", out, os.path.join(G, "53birds"), maf], capture_output=True, text=True)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
     for name in ["PhyloCSFpower"] + [f"PhyloCSF{k}" for k in FRAMES6] + [f"PhyloCSFRaw{k}" for k in FRAMES6]:
         bw = parse_bigwig(os.path.join(out, name + ".bw"))
         assert {v[0]: v[1] for v in bw["chroms"].values()} == CHROMS          # lengths taken from the MAF's srcSize fields

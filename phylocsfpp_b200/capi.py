@@ -13,6 +13,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libphylocsf_b200.so")
+if os.environ.get("PCSF_LIB_VARIANT"):          # kernel experiments (tools/build_variant.sh): lib/libphylocsf_b200_<variant>.so
+    LIB_PATH = os.path.join(_HERE, "lib", f"libphylocsf_b200_{os.environ['PCSF_LIB_VARIANT']}.so")
 
 PCSF_OK = 0
 PCSF_ERR_INVALID = 1

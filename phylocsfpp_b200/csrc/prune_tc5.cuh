@@ -23,6 +23,8 @@
 // kernel — neither compute a row index nor issue a copy.  (Round 1 streamed whole leaf tables through a shared-memory ring and
 // gathered from them with 2.6-way bank conflicts, 1000-2000 cycles per gather; letting the epilogue warps issue the cp.async
 // themselves cost ~1000 cycles per step on the critical path.)
+// (Round 2, measured and dropped: one 256-byte bulk TMA copy per row issued by the lane that owns the window, rows padded to 272 bytes:
+// ptxas serialises the 32 UBLKCP of a warp, 104 M against 122 M columns/s.)
 // The codon ids the row indices are computed from come from k_tc5_ids: one pass that writes, per pair of 128-window tiles, the
 // [chain][leaf][window] byte block the producers want in shared memory, so that a single bulk TMA copy brings it in (the
 // epilogue threads used to gather 3 bytes per leaf and window from the code matrix: 18 k cycles per pair with the tensor pipe idle).
@@ -50,7 +52,8 @@ constexpr int T5_TILE_BYTES = 32768;
 constexpr int T5_THREADS = 512;
 constexpr int T5_NPROD = 6;              // row producer warps (10..15)
 constexpr int T5_STACK_ENTRY_FLOATS = 64 * 128 + 128;   // 128 windows x 64 states + 128 exponents
-constexpr int T5_ROW_STAGE_BYTES = 128 * 256;           // one staging buffer of one chain: the rows of its 128 windows
+constexpr int T5_ROW_PITCH = 256;                       // XOR-swizzled 16-byte chunks, no padding
+constexpr int T5_ROW_STAGE_BYTES = 128 * T5_ROW_PITCH;  // one staging buffer of one chain: the rows of its 128 windows
 
 struct PruneTc5Args {
     const uint32_t *n_unique;
@@ -71,7 +74,7 @@ struct PruneTc5Args {
 __host__ __device__ inline size_t prune_tc5_smem_bytes(int nl, int n_steps, int n_src, int nstage, int nids) {
     size_t b = (size_t)nstage * T5_TILE_BYTES;
     b += (size_t)2 * 2 * T5_ROW_STAGE_BYTES;                // row staging: 2 chains x 2 buffers
-    b += (size_t)T5_NPROD * 128;                            // row index exchange, 32 x 4 bytes per producer warp
+    b += (size_t)T5_NPROD * 256;                            // row index exchange, 2 x 32 x 4 bytes per producer warp
     b += (size_t)nids * 2 * nl * 128;                       // codon ids of both tiles
     b += (size_t)(((n_steps + 1) * 4 + 15) / 16) * 16;      // steps
     b += (size_t)(n_src + 1) * sizeof(Tc5Src);              // sources
@@ -148,6 +151,13 @@ __global__ void __launch_bounds__(64) k_build_rows(const Tc5Src *__restrict__ sr
 __device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
+// the same copy allocating in L1: the 65 rows of a LEAF source (16.6 KB) are fetched ~4 times each per pair of tiles
+__device__ __forceinline__ void cp_async_16_ca(uint32_t dst_smem, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+#ifndef PCSF_TC5_ROWS_CA
+#define PCSF_TC5_ROWS_CA 2          // 0: every row copy bypasses L1, 1: all allocate in L1, 2: only the leaf sources' (measured 124.1 / 125.4 / 126.7 M columns/s)
+#endif
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -157,7 +167,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
     const uint32_t T5_NSTAGE = a.nstage;
     unsigned char *stage_buf = sp_; sp_ += (size_t)T5_NSTAGE * T5_TILE_BYTES;
     unsigned char *row_buf = sp_; sp_ += (size_t)2 * 2 * T5_ROW_STAGE_BYTES;       // [chain][buffer][128 rows][256 B]
-    uint32_t *row_xchg = reinterpret_cast<uint32_t *>(sp_); sp_ += (size_t)T5_NPROD * 128;
+    uint32_t *row_xchg = reinterpret_cast<uint32_t *>(sp_); sp_ += (size_t)T5_NPROD * 256;
     uint8_t *ids = sp_; sp_ += (size_t)a.nids * 2 * a.nl * 128;                    // [slot][chain][leaf][128]
     uint32_t *steps = reinterpret_cast<uint32_t *>(sp_); sp_ += (size_t)(((a.n_steps + 1) * 4 + 15) / 16) * 16;
     Tc5Src *srcs = reinterpret_cast<Tc5Src *>(sp_); sp_ += (size_t)(a.n_src + 1) * sizeof(Tc5Src);
@@ -174,15 +184,17 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #ifdef PCSF_TC5_TRACE
-    __shared__ long long trace[3][128][4];
-#define T5_TRACE(who, s, i) do { if (blockIdx.x == 0 && first_seq && (s) < 128) trace[who][s][i] = clock64(); } while (0)
+    __shared__ long long trace[3][64][4];
+    __shared__ long long ptrace[T5_NPROD][56][3];       // row producers: per job [before row_empty wait, after it, copies issued]
+    __shared__ unsigned short pjob[T5_NPROD][56];
+#define T5_TRACE(who, s, i) do { if (blockIdx.x == 0 && first_seq && (s) < 64) trace[who][s][i] = clock64(); } while (0)
 #else
 #define T5_TRACE(who, s, i) do { } while (0)
 #endif
     if (tid == 0) {
         for (int s = 0; s < T5_MAX_NSTAGE; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
         for (int c = 0; c < 2; ++c) { for (int k = 0; k < 2; ++k) mbar_init(a_ready + 2 * c + k, 128); mbar_init(d_ready + c, 1); }
-        for (int i = 0; i < 4; ++i) { mbar_init(row_full + i, 128); mbar_init(row_empty + i, 128); }   // 4 jobs x 32 lanes / 128 readers
+        for (int i = 0; i < 4; ++i) { mbar_init(row_full + i, 128); mbar_init(row_empty + i, 128); }   // 4 jobs (x 32 lanes) / 128 readers
         for (int i = 0; i < 2; ++i) { mbar_init(ids_full + i, 1); mbar_init(ids_empty + i, T5_NPROD); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -263,7 +275,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
             // (ch & 8) | ((ch ^ rr) & 7): the sixteen lanes that copy one row write two full 128-byte lines, and the eight threads of a
             // quarter warp that later read chunk j of their OWN rows (LDS.128) hit eight different bank groups.
             const int pw = warp - 10;
-            uint32_t *xchg = row_xchg + pw * 32;
+            uint32_t *xchg = row_xchg + pw * 64;
             const uint32_t row_s = tc5::smem_addr(row_buf);
             const int jobs_per_pair = n_src2 * 8;
             const int half = lane >> 4, ch = lane & 15;
@@ -298,27 +310,42 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
                     const uint32_t x = wid[(uint32_t)d.l1 * 128];
                     const uint32_t myrow = d.row_base + (d.l2 == 0xff ? x : x * 65u + wid[(uint32_t)d.l2 * 128]);
                     // every lane copies one 16-byte chunk of sixteen rows (lanes 0-15: the even windows, lanes 16-31: the odd ones): the row
-                    // indices change hands through 128 bytes of shared memory, even windows first
-                    xchg[(lane & 1) * 16 + (lane >> 1)] = myrow;
-                    __syncwarp();
-                    uint32_t rows[16];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint4 v = reinterpret_cast<const uint4 *>(xchg + half * 16)[k];
-                        rows[4 * k] = v.x; rows[4 * k + 1] = v.y; rows[4 * k + 2] = v.z; rows[4 * k + 3] = v.w;
-                    }
+                    // indices change hands through 128 bytes of shared memory, even windows first.  The exchange area is double-buffered
+                    // per warp (the __syncwarp of job J+1 orders the reads of job J before the writes of job J+2), and the indices are read
+                    // back four at a time right before their copies: an LDGSTS keeps its address registers until the LSU has taken the
+                    // request, and with the 40 registers of a producer warp ptxas used ONE register pair for all sixteen addresses, every
+                    // copy waiting for the previous one (~50 cycles each, 800-1000 per job: the rows arrived late, ncu source page).
+                    uint32_t *xb = xchg + (((J / T5_NPROD) & 1u) << 5);
+                    xb[(lane & 1) * 16 + (lane >> 1)] = myrow;
                     __syncwarp();
                     const uint32_t b = c * 2 + (G & 1);
+#ifdef PCSF_TC5_TRACE
+                    const uint32_t pj = (J - it * (uint32_t)jobs_per_pair) / T5_NPROD;
+                    const bool ptr_on = blockIdx.x == 0 && it == 4 && pj < 56 && lane == 0;
+                    if (ptr_on) { ptrace[pw][pj][0] = clock64(); pjob[pw][pj] = (unsigned short)j; }
+#endif
                     mbar_wait(row_empty + b, ((G >> 1) & 1) ^ 1);
+#ifdef PCSF_TC5_TRACE
+                    if (ptr_on) ptrace[pw][pj][1] = clock64();
+#endif
                     const float *tab = (m ? a.rowtab[1] : a.rowtab[0]) + ch * 4;
                     const uint32_t dst = row_s + b * T5_ROW_STAGE_BYTES + q * 32 * 256;
+                    const bool use_l1 = PCSF_TC5_ROWS_CA == 1 || (PCSF_TC5_ROWS_CA == 2 && d.l2 == 0xff);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int rr = 2 * i + half;                      // the window (row of the quarter) this lane copies a chunk of
-                        cp_async_16(dst + rr * 256 + (((ch & 8) | ((ch ^ rr) & 7)) << 4), tab + (size_t)rows[i] * 64);
+                    for (int k = 0; k < 4; ++k) {
+                        const uint4 v = reinterpret_cast<const uint4 *>(xb + half * 16)[k];
+                        const float *s0 = tab + (size_t)v.x * 64, *s1 = tab + (size_t)v.y * 64, *s2 = tab + (size_t)v.z * 64, *s3 = tab + (size_t)v.w * 64;
+                        const int r0 = 2 * (4 * k) + half, r1 = r0 + 2, r2 = r0 + 4, r3 = r0 + 6;          // the windows (rows of the quarter) of these four copies
+                        const uint32_t d0 = dst + r0 * 256 + (((ch & 8) | ((ch ^ r0) & 7)) << 4), d1 = dst + r1 * 256 + (((ch & 8) | ((ch ^ r1) & 7)) << 4),
+                                       d2 = dst + r2 * 256 + (((ch & 8) | ((ch ^ r2) & 7)) << 4), d3 = dst + r3 * 256 + (((ch & 8) | ((ch ^ r3) & 7)) << 4);
+                        if (use_l1) { cp_async_16_ca(d0, s0); cp_async_16_ca(d1, s1); cp_async_16_ca(d2, s2); cp_async_16_ca(d3, s3); }
+                        else { cp_async_16(d0, s0); cp_async_16(d1, s1); cp_async_16(d2, s2); cp_async_16(d3, s3); }
                     }
                     // the lane's arrival on the full barrier is triggered when all of its copies above have landed
                     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc5::smem_addr(row_full + b)) : "memory");
+#ifdef PCSF_TC5_TRACE
+                    if (ptr_on) ptrace[pw][pj][2] = clock64();
+#endif
                 }
                 __syncwarp();
                 if (lane == 0) { tc5::fence_proxy_async_smem(); mbar_arrive(ids_empty + slot); }   // the slot is refilled by TMA (async proxy)
@@ -332,7 +359,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
         float *stk = a.scratch + ((size_t)blockIdx.x * 2 + c) * (size_t)(a.max_stack > 0 ? a.max_stack : 1) * T5_STACK_ENTRY_FLOATS;
         uint32_t use = 0;
         uint32_t taken = 0;           // running source number of this chain (over all pairs of the CTA)
-        const unsigned char *rstage = row_buf + (size_t)c * 2 * T5_ROW_STAGE_BYTES + (size_t)t * 256;
+        const unsigned char *rstage = row_buf + (size_t)c * 2 * T5_ROW_STAGE_BYTES + (size_t)t * T5_ROW_PITCH;
         // L (= or *=) the staged message of this thread's window from the next source of the program
         auto take_row = [&](float (&L)[64], bool mul) {
             const uint32_t b = taken & 1;
@@ -563,9 +590,16 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
     }
 #ifdef PCSF_TC5_TRACE
     __syncwarp();
+    __syncthreads();
     if (blockIdx.x == 0 && tid == 0) {
         const long long t0 = trace[0][0][0];
-        for (int s = 0; s < a.n_steps && s < 128; ++s)
+        for (int w = 0; w < T5_NPROD; ++w)
+            for (int k = 0; k < 56 && k * T5_NPROD + w < a.n_src * 8; ++k) {
+                const int j = pjob[w][k];
+                printf("T5P warp %d job %3d src %2d chain %d q %d | start %7lld got-buffer %7lld (+%5lld) issued +%4lld\n", w, j, j >> 3, (j >> 2) & 1, j & 3,
+                       ptrace[w][k][0] - t0, ptrace[w][k][1] - t0, ptrace[w][k][1] - ptrace[w][k][0], ptrace[w][k][2] - ptrace[w][k][1]);
+            }
+        for (int s = 0; s < a.n_steps && s < 64; ++s)
             printf("T5 s=%3d post=%u | X: A-ready %7lld gather %5lld wait-D %5lld combine %5lld | Y: A-ready %7lld gather %5lld wait-D %5lld combine %5lld | MMA: aX %7lld issX %4lld aY %7lld issY %4lld\n",
                    s, (steps[s] >> 16) & 3u, trace[0][s][0] - t0, trace[0][s][1] - trace[0][s][0], trace[0][s][2] - trace[0][s][1],
                    trace[0][s][3] - trace[0][s][2], trace[1][s][0] - t0, trace[1][s][1] - trace[1][s][0], trace[1][s][2] - trace[1][s][1],

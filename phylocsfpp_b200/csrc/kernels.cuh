@@ -645,47 +645,89 @@ __global__ void k_scatter_list(uint32_t nwin, const uint32_t *__restrict__ pidx,
 // newick_sum_branch_lengths (additional_scores.hpp:5-41) => bit-identical doubles.
 // raw != 0: write bl(S) itself (score-msa sums it, :71), else bl(S)/bl(all) (:73-74).
 constexpr int BLS_THREADS = 128;
+constexpr int BLS_COLS = 4;            // columns per thread: one 32-bit load per species, four independent evaluations in flight
 
 __global__ void __launch_bounds__(BLS_THREADS) k_bls(const uint8_t *__restrict__ codes, int64_t ld, int nl, int64_t L,
-                                                    const BlsInner *__restrict__ prog, int n_inner, int depth,
-                                                    double all, int raw, double *__restrict__ out) {
-    extern __shared__ double bls_stack[];  // [depth][BLS_THREADS]
-    const int64_t i = (int64_t)blockIdx.x * BLS_THREADS + threadIdx.x;
-    if (i >= L) return;
-    uint64_t mlo = 0, mhi = 0;
-    int cnt = 0;
+                                                    const BlsInner *__restrict__ prog, int n_prog, int depth,
+                                                    const double *__restrict__ tables, double all, int raw, double *__restrict__ out) {
+    extern __shared__ double bls_stack[];  // [depth][BLS_COLS][BLS_THREADS]
+    const int64_t i0 = ((int64_t)blockIdx.x * BLS_THREADS + threadIdx.x) * BLS_COLS;
+    if (i0 >= L) return;
+    // presence masks of four consecutive columns (rows are padded with N up to a multiple of 16 columns, so the word load is safe)
+    uint64_t mlo[BLS_COLS] = {0, 0, 0, 0}, mhi[BLS_COLS] = {0, 0, 0, 0};
     for (int s = 0; s < nl; ++s) {
-        const uint32_t c = codes[(int64_t)s * ld + i];
-        if (c <= 3) {
-            if (s < 64) mlo |= 1ull << s; else mhi |= 1ull << (s - 64);
-            ++cnt;
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(codes + (int64_t)s * ld + i0));
+        const uint32_t present = ~(w >> 2) & 0x01010101u;          // code <= 3 (A, C, G, T): bit 2 clear
+        if (s < 64) {
+#pragma unroll
+            for (int j = 0; j < BLS_COLS; ++j) mlo[j] |= (uint64_t)((present >> (8 * j)) & 1u) << s;
+        } else {
+#pragma unroll
+            for (int j = 0; j < BLS_COLS; ++j) mhi[j] |= (uint64_t)((present >> (8 * j)) & 1u) << (s - 64);
         }
     }
-    double res = 0.0;
-    if (cnt >= 2) {
-        // inner nodes in post-order; a leaf child contributes its own branch length (no stack traffic), an inner child the value on
-        // top of the stack (right child first: it was evaluated last).  Summation order = the reference's: (own + left) + right.
-        double *st = bls_stack + threadIdx.x;
-        int sp = 0;
-        double v = 0.0;
-        for (int k = 0; k < n_inner; ++k) {
-            const BlsInner e = prog[k];
-            double r, l;
-            if (e.flags & 2) r = e.right_bl; else { --sp; r = st[sp * BLS_THREADS]; }
-            if (e.flags & 1) l = e.left_bl; else { --sp; l = st[sp * BLS_THREADS]; }
-            const bool ol = ((mlo & e.left_lo) | (mhi & e.left_hi)) != 0;
-            const bool orr = ((mlo & e.self_lo & ~e.left_lo) | (mhi & e.self_hi & ~e.left_hi)) != 0;
-            const bool arrived = ((mlo & ~e.self_lo) | (mhi & ~e.self_hi)) != 0;
-            v = arrived ? e.bl : 0.0;
-            if (ol) v = __dadd_rn(v, l);
-            if (orr) v = __dadd_rn(v, r);
-            st[sp * BLS_THREADS] = v;
-            ++sp;
+    // inner nodes in post-order; a leaf child contributes its own branch length (no stack traffic), an inner child the value on
+    // top of the stack (right child first: it was evaluated last).  Summation order = the reference's: (own + left) + right.
+    // A TABLE entry (model_prep.hpp: bls_build_tables) pushes the tabulated value of a whole subtree of <= 12 leaves.
+    double *st = bls_stack + threadIdx.x;
+    int sp = 0;
+    double v[BLS_COLS] = {0.0, 0.0, 0.0, 0.0};
+    for (int k = 0; k < n_prog; ++k) {
+        const BlsInner e = prog[k];
+        if (e.flags & 4) {
+            const int shift = (e.flags >> 8) & 0xff, nbits = (e.flags >> 16) & 0xff;
+#pragma unroll
+            for (int j = 0; j < BLS_COLS; ++j) {
+                const bool arrived = ((mlo[j] & ~e.self_lo) | (mhi[j] & ~e.self_hi)) != 0;
+                uint64_t bits;
+                if (shift >= 64) bits = mhi[j] >> (shift - 64);
+                else bits = (mlo[j] >> shift) | (shift ? mhi[j] << (64 - shift) : 0ull);
+                bits &= (1ull << nbits) - 1;
+                v[j] = __ldg(tables + e.tab_off + 2 * bits + (arrived ? 1 : 0));
+            }
+        } else {
+            double r[BLS_COLS], l[BLS_COLS];
+            if (e.flags & 2) {
+#pragma unroll
+                for (int j = 0; j < BLS_COLS; ++j) r[j] = e.right_bl;
+            } else {
+                --sp;
+#pragma unroll
+                for (int j = 0; j < BLS_COLS; ++j) r[j] = st[(sp * BLS_COLS + j) * BLS_THREADS];
+            }
+            if (e.flags & 1) {
+#pragma unroll
+                for (int j = 0; j < BLS_COLS; ++j) l[j] = e.left_bl;
+            } else {
+                --sp;
+#pragma unroll
+                for (int j = 0; j < BLS_COLS; ++j) l[j] = st[(sp * BLS_COLS + j) * BLS_THREADS];
+            }
+#pragma unroll
+            for (int j = 0; j < BLS_COLS; ++j) {
+                const bool arrived = ((mlo[j] & ~e.self_lo) | (mhi[j] & ~e.self_hi)) != 0;
+                const bool ol = ((mlo[j] & e.left_lo) | (mhi[j] & e.left_hi)) != 0;
+                const bool orr = ((mlo[j] & e.self_lo & ~e.left_lo) | (mhi[j] & e.self_hi & ~e.left_hi)) != 0;
+                double x = arrived ? e.bl : 0.0;
+                if (ol) x = __dadd_rn(x, l[j]);
+                if (orr) x = __dadd_rn(x, r[j]);
+                v[j] = x;
+            }
         }
-        res = v;
-        if (!raw) res = __ddiv_rn(res, all);
+#pragma unroll
+        for (int j = 0; j < BLS_COLS; ++j) st[(sp * BLS_COLS + j) * BLS_THREADS] = v[j];
+        ++sp;
     }
-    out[i] = res;
+#pragma unroll
+    for (int j = 0; j < BLS_COLS; ++j) {
+        if (i0 + j >= L) break;
+        double res = 0.0;
+        if (__popcll(mlo[j]) + __popcll(mhi[j]) >= 2) {          // fewer than two species with a base: 0 (additional_scores.hpp:66-69)
+            res = v[j];
+            if (!raw) res = __ddiv_rn(res, all);
+        }
+        out[i0 + j] = res;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -42,8 +42,11 @@ struct BlsInner {           // one INNER node of the BLS program, post-order; le
     double left_bl, right_bl;    // the child's branch length if it is a leaf
     uint64_t self_lo, self_hi;
     uint64_t left_lo, left_hi;
-    int32_t flags;          // bit 0: left child is a leaf, bit 1: right child is a leaf
-    int32_t pad;
+    int32_t flags;          // bit 0: left child is a leaf, bit 1: right child is a leaf;
+                            // bit 2: TABLE entry — the value of this node for every presence pattern of its (<= BLS_TABLE_BITS, consecutively
+                            // numbered) leaves and for arrived = 0 / 1 was tabulated on the host with the very same additions: the device
+                            // pushes tables[tab_off + 2 * pattern + arrived]; bits 8-15: number of the first leaf, bits 16-23: leaf count
+    int32_t tab_off;
 };
 
 struct EcmHost {
@@ -89,6 +92,9 @@ struct ModelHost {
     int tc5_max_stack = 0;             // pushes alive at once (depth of the global-memory stack)
     std::vector<BlsNode> bls_prog;
     std::vector<BlsInner> bls_inner;
+    std::vector<BlsInner> bls_short;      // the program k_bls runs: subtrees of <= BLS_TABLE_BITS leaves collapsed into TABLE entries
+    std::vector<double> bls_tables;
+    int bls_short_depth = 0;
     int bls_depth = 0;
     double bls_all = 0.0;         // all_species_branch_length (additional_scores.hpp:56)
 };
@@ -454,6 +460,124 @@ inline double bls_eval_host(const ModelHost &m, uint64_t mlo, uint64_t mhi) {
     return st[0];
 }
 
+// The inner-node program (what k_bls executed before the tables): value on top of the stack right after entry `upto`.
+inline double bls_eval_inner_host(const std::vector<BlsInner> &prog, int depth, uint64_t mlo, uint64_t mhi, int upto) {
+    std::vector<double> st(depth + 2);
+    int sp = 0;
+    double v = 0.0;
+    for (int k = 0; k <= upto; ++k) {
+        const BlsInner &e = prog[k];
+        double r, l;
+        if (e.flags & 2) r = e.right_bl; else r = st[--sp];
+        if (e.flags & 1) l = e.left_bl; else l = st[--sp];
+        const bool ol = ((mlo & e.left_lo) | (mhi & e.left_hi)) != 0;
+        const bool orr = ((mlo & e.self_lo & ~e.left_lo) | (mhi & e.self_hi & ~e.left_hi)) != 0;
+        const bool arrived = ((mlo & ~e.self_lo) | (mhi & ~e.self_hi)) != 0;
+        v = arrived ? e.bl : 0.0;
+        if (ol) v += l;
+        if (orr) v += r;
+        st[sp++] = v;
+    }
+    return v;
+}
+
+constexpr int BLS_TABLE_BITS = 12;
+
+// Collapses every maximal subtree of <= BLS_TABLE_BITS leaves into one TABLE entry.  A node's value depends only on which of ITS leaves
+// are present and on whether any leaf outside is (arrived): 2^k x 2 doubles, computed by the inner-node program itself, so the
+// device reads exactly the doubles it would have summed (58mammals: 16 entries instead of 57, 113 KB of tables).
+inline void bls_build_tables(ModelHost &m) {
+    m.bls_short.clear();
+    m.bls_tables.clear();
+    const int n_inner = (int)m.bls_inner.size();
+    auto popcnt = [](uint64_t x) { return __builtin_popcountll(x); };
+    // post-order program: the subtree of entry k is a contiguous run of entries ending at k; find its first entry by counting
+    std::vector<int> first(n_inner);
+    {
+        std::vector<int> stack;          // start index of the run of every value currently on the stack
+        for (int k = 0; k < n_inner; ++k) {
+            const BlsInner &e = m.bls_inner[k];
+            int f = k;
+            if (!(e.flags & 2)) { f = std::min(f, stack.back()); stack.pop_back(); }
+            if (!(e.flags & 1)) { f = std::min(f, stack.back()); stack.pop_back(); }
+            first[k] = f;
+            stack.push_back(f);
+        }
+    }
+    std::vector<char> is_root(n_inner, 0);
+    for (int k = n_inner - 1; k >= 0; --k) {
+        const BlsInner &e = m.bls_inner[k];
+        if (popcnt(e.self_lo) + popcnt(e.self_hi) > BLS_TABLE_BITS) continue;
+        bool inside = false;             // already inside a collapsed subtree?
+        for (int r = k + 1; r < n_inner && !inside; ++r) inside = is_root[r] && first[r] <= k;
+        if (!inside) is_root[k] = 1;
+    }
+    const uint64_t alo = m.nl >= 64 ? ~0ull : ((1ull << m.nl) - 1);
+    const uint64_t ahi = m.nl > 64 ? (m.nl >= 128 ? ~0ull : ((1ull << (m.nl - 64)) - 1)) : 0ull;
+    for (int k = 0; k < n_inner; ++k) {
+        bool dropped = false;
+        for (int r = k + 1; r < n_inner && !dropped; ++r) dropped = is_root[r] && first[r] <= k;
+        if (dropped) continue;
+        BlsInner e = m.bls_inner[k];
+        if (is_root[k]) {
+            const int nbits = popcnt(e.self_lo) + popcnt(e.self_hi);
+            const int shift = e.self_lo ? __builtin_ctzll(e.self_lo) : 64 + __builtin_ctzll(e.self_hi);
+            // one leaf outside the subtree stands for "arrived" (none exists when the subtree is the whole tree: arrived is never set)
+            const uint64_t olo = alo & ~e.self_lo, ohi = ahi & ~e.self_hi;
+            uint64_t wlo = 0, whi = 0;
+            if (olo) wlo = olo & (~olo + 1); else if (ohi) whi = ohi & (~ohi + 1);
+            e.flags = 4 | (shift << 8) | (nbits << 16);
+            e.tab_off = (int32_t)m.bls_tables.size();
+            for (uint64_t pat = 0; pat < (1ull << nbits); ++pat)
+                for (int arrived = 0; arrived < 2; ++arrived) {
+                    unsigned __int128 bits = (unsigned __int128)pat << shift;
+                    uint64_t mlo = (uint64_t)bits, mhi = (uint64_t)(bits >> 64);
+                    if (arrived) { mlo |= wlo; mhi |= whi; }
+                    m.bls_tables.push_back(bls_eval_inner_host(m.bls_inner, m.bls_depth, mlo, mhi, k));
+                }
+        }
+        m.bls_short.push_back(e);
+    }
+    // stack depth of the short program
+    int sp = 0, depth = 1;
+    for (const BlsInner &e : m.bls_short) {
+        if (!(e.flags & 4)) { if (!(e.flags & 2)) --sp; if (!(e.flags & 1)) --sp; }
+        ++sp;
+        depth = std::max(depth, sp);
+    }
+    m.bls_short_depth = depth;
+    if (m.bls_tables.empty()) m.bls_tables.push_back(0.0);
+}
+
+// What k_bls executes, on the host (self-check at model creation).
+inline double bls_eval_short_host(const ModelHost &m, uint64_t mlo, uint64_t mhi) {
+    std::vector<double> st(m.bls_short_depth + 2);
+    int sp = 0;
+    double v = 0.0;
+    for (const BlsInner &e : m.bls_short) {
+        const bool arrived = ((mlo & ~e.self_lo) | (mhi & ~e.self_hi)) != 0;
+        if (e.flags & 4) {
+            const int shift = (e.flags >> 8) & 0xff, nbits = (e.flags >> 16) & 0xff;
+            uint64_t bits;
+            if (shift >= 64) bits = mhi >> (shift - 64);
+            else bits = (mlo >> shift) | (shift ? mhi << (64 - shift) : 0ull);
+            bits &= (1ull << nbits) - 1;
+            v = m.bls_tables[(size_t)e.tab_off + 2 * bits + (arrived ? 1 : 0)];
+        } else {
+            double r, l;
+            if (e.flags & 2) r = e.right_bl; else r = st[--sp];
+            if (e.flags & 1) l = e.left_bl; else l = st[--sp];
+            const bool ol = ((mlo & e.left_lo) | (mhi & e.left_hi)) != 0;
+            const bool orr = ((mlo & e.self_lo & ~e.left_lo) | (mhi & e.self_hi & ~e.left_hi)) != 0;
+            v = arrived ? e.bl : 0.0;
+            if (ol) v += l;
+            if (orr) v += r;
+        }
+        st[sp++] = v;
+    }
+    return v;
+}
+
 // Returns "" on success.
 inline std::string prepare_model(ModelHost &m, int nl, const int16_t *c1, const int16_t *c2, const float *bl,
                                  const double *bl64, const double *const S[2], const double *const f[2]) {
@@ -486,6 +610,22 @@ inline std::string prepare_model(ModelHost &m, int nl, const int16_t *c1, const 
         const uint64_t alo = nl >= 64 ? ~0ull : ((1ull << nl) - 1);
         const uint64_t ahi = nl > 64 ? (nl >= 128 ? ~0ull : ((1ull << (nl - 64)) - 1)) : 0ull;
         m.bls_all = bls_eval_host(m, alo, ahi);
+    }
+    bls_build_tables(m);
+    {   // the collapsed program must give the node-by-node program's doubles, bit for bit
+        uint64_t x = 0x9E3779B97F4A7C15ull;
+        const uint64_t alo = nl >= 64 ? ~0ull : ((1ull << nl) - 1);
+        const uint64_t ahi = nl > 64 ? (nl >= 128 ? ~0ull : ((1ull << (nl - 64)) - 1)) : 0ull;
+        for (int t = 0; t < 2000; ++t) {
+            x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+            uint64_t mlo = x; x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+            uint64_t mhi = x;
+            if (t % 3 == 1) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; mlo &= x; x ^= x << 13; x ^= x >> 7; x ^= x << 17; mhi &= x; }   // sparse masks
+            if (t % 3 == 2) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; mlo |= x; x ^= x << 13; x ^= x >> 7; x ^= x << 17; mhi |= x; }   // dense masks
+            mlo &= alo; mhi &= ahi;
+            const double a = bls_eval_host(m, mlo, mhi), b = bls_eval_short_host(m, mlo, mhi);
+            if (memcmp(&a, &b, 8) != 0) return "internal error: BLS tables disagree with the node-by-node program";
+        }
     }
     // the two ECMs
     for (int w = 0; w < 2; ++w) {

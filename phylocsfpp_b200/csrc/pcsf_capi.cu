@@ -89,6 +89,7 @@ struct pcsf_model {
     DevBuf tc5_ids;                      // codon ids of the unique windows, [pairs][2][nl][128] (k_tc5_ids)
     int32_t *d_program = nullptr;
     BlsInner *d_bls_prog = nullptr;
+    double *d_bls_tables = nullptr;
     float *d_bl = nullptr;
     int32_t *d_gemm_edges = nullptr;
     // scratch
@@ -190,7 +191,8 @@ extern "C" pcsf_status pcsf_model_create(const pcsf_model_desc *d, int device, p
     if (const char *e = getenv("PCSF_TC5_NIDS")) m->tc5_nids = std::max(1, std::min(m->tc5_nids, atoi(e)));
     m->prune_tc5_smem = prune_tc5_smem_bytes(m->host.nl, (int)m->host.tc5_steps.size(), (int)m->host.tc5_srcs.size(), m->tc5_nstage, m->tc5_nids);
     CK(cudaFuncSetAttribute(k_prune_tc5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->prune_tc5_smem));
-    if ((st = upload(m->host.bls_inner.data(), m->host.bls_inner.size() * sizeof(BlsInner), (void **)&m->d_bls_prog))) return st;
+    if ((st = upload(m->host.bls_short.data(), m->host.bls_short.size() * sizeof(BlsInner), (void **)&m->d_bls_prog))) return st;
+    if ((st = upload(m->host.bls_tables.data(), std::max<size_t>(m->host.bls_tables.size(), 1) * sizeof(double), (void **)&m->d_bls_tables))) return st;
     if ((st = upload(m->host.bl.data(), m->host.bl.size() * 4, (void **)&m->d_bl))) return st;
     {
         std::vector<int32_t> ge(m->host.gemm_edges.begin(), m->host.gemm_edges.end());
@@ -219,7 +221,7 @@ extern "C" pcsf_status pcsf_model_create(const pcsf_model_desc *d, int device, p
     CK(cudaFuncSetAttribute(k_prune<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->prune_smem));
     CK(cudaFuncSetAttribute(k_prune<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->prune_smem));
     CK(cudaFuncSetAttribute(k_bls, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            std::max(1, m->host.bls_depth) * BLS_THREADS * 8));
+                            std::max(1, m->host.bls_short_depth) * BLS_THREADS * BLS_COLS * 8));
     guard.m = nullptr;
     *out = m;
     return PCSF_OK;
@@ -232,7 +234,7 @@ extern "C" void pcsf_model_destroy(pcsf_model *m) {
         cudaFree(m->d_pstream[w]); cudaFree(m->d_leafPT[w]); cudaFree(m->d_rowtab_tc5[w]); cudaFree(m->d_pstream_tc5[w]); cudaFree(m->d_pi[w]); cudaFree(m->d_logpi[w]);
         cudaFree(m->d_eig[w]);
     }
-    cudaFree(m->d_program); cudaFree(m->d_bls_prog); cudaFree(m->d_bl); cudaFree(m->d_gemm_edges);
+    cudaFree(m->d_program); cudaFree(m->d_bls_prog); cudaFree(m->d_bls_tables); cudaFree(m->d_bl); cudaFree(m->d_gemm_edges);
     cudaFree(m->d_bad); cudaFree(m->d_nuniq); cudaFree(m->d_tc5_steps); cudaFree(m->d_tc5_scratch); cudaFree(m->d_tc5_srcs);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
@@ -425,10 +427,10 @@ static pcsf_status run_pack(pcsf_model *m, const uint8_t *d_seqs, int64_t L, int
 static pcsf_status run_bls(pcsf_model *m, int64_t L, int raw, double *d_out, cudaStream_t st) {
     if (L <= 0) return PCSF_OK;
     NvtxRange nvtx_("pcsf: bls");
-    const size_t sh = (size_t)std::max(1, m->host.bls_depth) * BLS_THREADS * 8;
-    m->launches++; k_bls<<<(unsigned)((L + BLS_THREADS - 1) / BLS_THREADS), BLS_THREADS, sh, st>>>(
-        m->codes.as<uint8_t>(), m->codes_ld, m->host.nl, L, m->d_bls_prog, (int)m->host.bls_inner.size(),
-        m->host.bls_depth, m->host.bls_all, raw, d_out);
+    const size_t sh = (size_t)std::max(1, m->host.bls_short_depth) * BLS_THREADS * BLS_COLS * 8;
+    m->launches++; k_bls<<<(unsigned)((L + BLS_THREADS * BLS_COLS - 1) / (BLS_THREADS * BLS_COLS)), BLS_THREADS, sh, st>>>(
+        m->codes.as<uint8_t>(), m->codes_ld, m->host.nl, L, m->d_bls_prog, (int)m->host.bls_short.size(),
+        m->host.bls_short_depth, m->d_bls_tables, m->host.bls_all, raw, d_out);
     CK(cudaGetLastError());
     return PCSF_OK;
 }
@@ -444,10 +446,10 @@ static pcsf_status run_pack_segment(pcsf_model *m, const uint8_t *d_seqs, int64_
 }
 static pcsf_status run_bls_segment(pcsf_model *m, int64_t s0, int64_t s1, double *d_out, cudaStream_t st) {
     if (s1 <= s0) return PCSF_OK;
-    const size_t sh = (size_t)std::max(1, m->host.bls_depth) * BLS_THREADS * 8;
-    m->launches++; k_bls<<<(unsigned)((s1 - s0 + BLS_THREADS - 1) / BLS_THREADS), BLS_THREADS, sh, st>>>(
-        m->codes.as<uint8_t>() + s0, m->codes_ld, m->host.nl, s1 - s0, m->d_bls_prog, (int)m->host.bls_inner.size(),
-        m->host.bls_depth, m->host.bls_all, 0, d_out + s0);
+    const size_t sh = (size_t)std::max(1, m->host.bls_short_depth) * BLS_THREADS * BLS_COLS * 8;
+    m->launches++; k_bls<<<(unsigned)((s1 - s0 + BLS_THREADS * BLS_COLS - 1) / (BLS_THREADS * BLS_COLS)), BLS_THREADS, sh, st>>>(
+        m->codes.as<uint8_t>() + s0, m->codes_ld, m->host.nl, s1 - s0, m->d_bls_prog, (int)m->host.bls_short.size(),
+        m->host.bls_short_depth, m->d_bls_tables, m->host.bls_all, 0, d_out + s0);
     CK(cudaGetLastError());
     return PCSF_OK;
 }

@@ -182,3 +182,7 @@ def test_tcgen05_step_program_on_the_cpu(tc5_check_exe, model, species):
     d64 = float(re.search(r"max \|d log z\| = (\S+)", r.stdout).group(1))
     d32 = float(re.search(r"max \|d\| = (\S+) decibans", r.stdout).group(1))
     assert d64 < 1e-11 and d32 < 2e-4, r.stdout
+    # k_bls's program with tabulated subtrees: prepare_model itself compares it bit for bit with the node-by-node program on 2000
+    # presence masks (a mismatch is an error above); here: it really is shorter
+    mb = re.search(r"BLS program: (\d+) entries \((\d+) tables, (\d+) doubles\) for (\d+) inner nodes", r.stdout)
+    assert mb and int(mb.group(2)) >= 1 and int(mb.group(1)) <= max(1, (int(mb.group(4)) + 1) // 2), r.stdout

@@ -160,6 +160,12 @@ int main(int argc, char **argv) {
     const double *S[2] = {hm.c.S.data(), hm.nc.S.data()}, *f[2] = {hm.c.f.data(), hm.nc.f.data()};
     const std::string err = prepare_model(m, hm.tree.nl, hm.tree.child1.data(), hm.tree.child2.data(), hm.tree.bl.data(), hm.tree.bl64.data(), S, f);
     if (!err.empty()) host::die("%s", err.c_str());
+    {   // the BLS program with tabulated subtrees (prepare_model has already compared it with the node-by-node program on 2000 masks)
+        int n_tab = 0;
+        for (const BlsInner &e : m.bls_short) n_tab += (e.flags & 4) != 0;
+        printf("BLS program: %zu entries (%d tables, %zu doubles) for %zu inner nodes, stack depth %d (was %d)\n", m.bls_short.size(), n_tab,
+               m.bls_tables.size(), m.bls_inner.size(), m.bls_short_depth, m.bls_depth);
+    }
     std::mt19937 rng(12345);
     std::uniform_real_distribution<double> U(0, 1);
     double worst = 0.0, worst32 = 0.0;

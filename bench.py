@@ -177,6 +177,15 @@ class ClockSampler:
 SPECIES12 = "Human,Chimp,Mouse,Dog,Cow,Horse,Elephant,Armadillo,Rat,Rabbit,Cat,Megabat"
 
 
+def kernel_sha16() -> str:
+    """Hash of the sources of k_prune_tc5 (what a committed ncu capture is stamped with)."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("prune_tc5.cuh", "tc5.cuh"):
+        h.update(open(os.path.join(ROOT, "phylocsfpp_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def n_tc5_gemms(tree) -> int:
     """GEMMs per pruning on the tcgen05 path: inner edges that are not cherries (a cherry's message is a table row)."""
     c1, c2, nl, n = tree.child1, tree.child2, tree.nl, tree.n
@@ -647,10 +656,13 @@ def main():
             traffic = tj.get({"f64": "dram_bytes_per_launch", "f32": "dram_bytes_per_launch_f32", "tc5": "dram_bytes_per_launch_tc5"}[args.precision])
             cap_cols = tj.get("tc5_columns_per_captured_launch") if args.precision == "tc5" else None
             if traffic and cap_cols:
-                # the ncu --set full capture ran on a smaller batch; DRAM traffic of this kernel (leaf codes in, log z out) is linear
-                # in the columns of a launch
+                # the ncu --set full capture ran on a smaller batch; DRAM traffic of this kernel (codon ids in, log z out) is linear
+                # in the columns of a launch.  The capture is stamped with the hash of the kernel's sources (tools/ncu_traffic_stamp.py):
+                # a kernel edited since then gets no traffic figure rather than a stale one.
                 traffic = traffic * (B / n_prune_launch) / cap_cols
-                traffic_note = f"dram__bytes_read+write of one ncu --set full capture at {cap_cols} columns per launch, scaled to {B // n_prune_launch}"
+                traffic_note = f"dram__bytes_read+write of one ncu --set full capture ({tj.get('tc5_source')}) at {cap_cols} columns per launch, scaled to {B // n_prune_launch}"
+                if args.precision == "tc5" and tj.get("tc5_kernel_sha16") != kernel_sha16():
+                    traffic, traffic_note = None, "the committed ncu capture predates the current kernel sources (profiles/ncu_prune_traffic.json: tc5_kernel_sha16)"
         except Exception:
             pass
         if args.precision == "f64":

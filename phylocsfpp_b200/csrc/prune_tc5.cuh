@@ -308,7 +308,11 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
                     const Tc5Src d = srcs[g - m * a.n_src];
                     const uint8_t *wid = pids + (size_t)c * a.nl * 128 + q * 32 + lane;
                     const uint32_t x = wid[(uint32_t)d.l1 * 128];
+#if defined(PCSF_TC5_EXP) && PCSF_TC5_EXP == 2
+                    const uint32_t myrow = d.row_base + (x & 0u) + q * 32 + lane;          // timing experiment: 32 consecutive rows (wrong results)
+#else
                     const uint32_t myrow = d.row_base + (d.l2 == 0xff ? x : x * 65u + wid[(uint32_t)d.l2 * 128]);
+#endif
                     // every lane copies one 16-byte chunk of sixteen rows (lanes 0-15: the even windows, lanes 16-31: the odd ones): the row
                     // indices change hands through 128 bytes of shared memory, even windows first.  The exchange area is double-buffered
                     // per warp (the __syncwarp of job J+1 orders the reads of job J before the writes of job J+2), and the indices are read
@@ -331,6 +335,11 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_prune_tc5(const PruneTc5Args 
                     const float *tab = (m ? a.rowtab[1] : a.rowtab[0]) + ch * 4;
                     const uint32_t dst = row_s + b * T5_ROW_STAGE_BYTES + q * 32 * 256;
                     const bool use_l1 = PCSF_TC5_ROWS_CA == 1 || (PCSF_TC5_ROWS_CA == 2 && d.l2 == 0xff);
+#if defined(PCSF_TC5_EXP) && PCSF_TC5_EXP == 1
+                    mbar_arrive(row_full + b);          // timing experiment: no copies at all (wrong results)
+                    (void)tab; (void)dst; (void)use_l1;
+                    continue;
+#endif
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint4 v = reinterpret_cast<const uint4 *>(xb + half * 16)[k];

@@ -198,33 +198,72 @@ public:
         std::vector<uint8_t> present(nl);
         std::vector<std::pair<size_t, size_t>> runs;
         std::string key;
+        // Species of the previous block, line by line: consecutive blocks of a MAF list mostly the same species in the same order, so the
+        // species token of line k is first compared with what line k of the previous block resolved to (one short memcmp instead of
+        // lower-casing + hashing); -2 = "not in the model".
+        struct Seen { const char *name; int len; int id; };
+        std::vector<Seen> prev_lines, cur_lines;
         for (size_t bi : c.blocks) {
             const BlockMeta &b = blocks_[bi];
             const char *p = mem_ + b.off, *end = mem_ + b.end;
             rows.clear();
+            cur_lines.clear();
             std::fill(present.begin(), present.end(), 0);
             const Row *ref = nullptr;
             while (p < end) {
                 const char *nlp = (const char *)memchr(p, '\n', (size_t)(end - p));
                 const char *le = nlp ? nlp : end;
                 if (*p == 's') {
+                    // Only two tokens matter here: the species (token 1, up to the first '.') and the sequence text (token 6).  The text
+                    // is the last token of a well-formed line, so it is found from the line's end; lines with fewer than seven tokens or
+                    // with anything behind the text take the full tokeniser, which is what the scan and read_chain() use.
+                    const char *q = p + 1;
+                    while (q < le && *q == ' ') ++q;
+                    const char *id0 = q;
+                    while (q < le && *q != ' ') ++q;
+                    const char *id1 = q;
+                    const char *e2 = le;
+                    while (e2 > id1 && e2[-1] == '\r') --e2;
+                    const char *sp = e2 > id1 ? (const char *)memrchr(id1, ' ', (size_t)(e2 - id1)) : nullptr;
                     SLine s;
-                    if (parse_s_line(p, le, s)) {
+                    bool ok = false;
+                    if (sp && sp + 1 < e2 && p + 1 < le && p[1] == ' ') {
+                        // count the tokens between the identifier and the text: exactly four (start, size, strand, srcSize)
+                        int ntok = 0;
+                        for (const char *r = id1; r < sp;) {
+                            while (r < sp && *r == ' ') ++r;
+                            if (r >= sp) break;
+                            ++ntok;
+                            while (r < sp && *r != ' ') ++r;
+                        }
+                        if (ntok == 4 && id1 > id0) { s.ident = id0; s.ident_len = (int)(id1 - id0); s.seq = sp + 1; s.seq_len = (size_t)(e2 - sp - 1); ok = true; }
+                    }
+                    if (!ok) ok = parse_s_line(p, le, s);
+                    if (ok) {
                         const char *dot = (const char *)memchr(s.ident, '.', (size_t)s.ident_len);
                         const int sl = dot ? (int)(dot - s.ident) : s.ident_len;
-                        key.assign(s.ident, (size_t)sl);
-                        for (char &ch : key) ch = (char)tolower((unsigned char)ch);
-                        auto it = model_.seqid_to_phyloid.find(key);
-                        if (it != model_.seqid_to_phyloid.end()) {
-                            if (present[it->second]) die("alignment rows of different length in block at byte %zu", b.off);
-                            present[it->second] = 1;
-                            rows.push_back(Row{(int)it->second, s.seq, s.seq_len});
-                            if (species_seen) (*species_seen)[it->second] = 1;
+                        int id = -1;
+                        const size_t k = cur_lines.size();
+                        if (k < prev_lines.size() && prev_lines[k].len == sl && memcmp(prev_lines[k].name, s.ident, (size_t)sl) == 0) {
+                            id = prev_lines[k].id;
+                        } else {
+                            key.assign(s.ident, (size_t)sl);
+                            for (char &ch : key) ch = (char)tolower((unsigned char)ch);
+                            auto it = model_.seqid_to_phyloid.find(key);
+                            id = it != model_.seqid_to_phyloid.end() ? (int)it->second : -2;
+                        }
+                        cur_lines.push_back(Seen{s.ident, sl, id});
+                        if (id >= 0) {
+                            if (present[id]) die("alignment rows of different length in block at byte %zu", b.off);
+                            present[id] = 1;
+                            rows.push_back(Row{id, s.seq, s.seq_len});
+                            if (species_seen) (*species_seen)[id] = 1;
                         }
                     }
                 }
                 p = le + 1;
             }
+            prev_lines.swap(cur_lines);
             for (const Row &r : rows) if (r.id == c.ref_id) { ref = &r; break; }
             if (!ref) continue;                                   // a block without the reference species adds no column
             const size_t alen = ref->len;
@@ -280,11 +319,16 @@ private:
         }
         pos = next_block(pos);
         std::string key;
+        // species of the previous block's `s` lines (see read_chain_into): line k of a block usually names the species line k of the
+        // previous block named, and then neither the lower-casing nor the hash lookup is needed
+        struct Seen { const char *name; int len; bool known; };
+        std::vector<Seen> prev_lines, cur_lines;
         while (pos < to && pos < size_) {
             BlockMeta b;
             b.off = pos;
             const char *q = (const char *)memchr(mem_ + pos, '\n', size_ - pos);
             size_t p = q ? (size_t)(q - mem_) + 1 : size_;
+            cur_lines.clear();
             while (p < size_ && !at_block(p)) {
                 const char *nlp = (const char *)memchr(mem_ + p, '\n', size_ - p);
                 const size_t le = nlp ? (size_t)(nlp - mem_) : size_;
@@ -297,6 +341,7 @@ private:
                         key.assign(s.ident, (size_t)sl);
                         for (char &ch : key) ch = (char)tolower((unsigned char)ch);
                         auto it = model_.seqid_to_phyloid.find(key);
+                        cur_lines.push_back(Seen{s.ident, sl, it != model_.seqid_to_phyloid.end()});
                         if (it == model_.seqid_to_phyloid.end()) {
                             b.pre.push_back(PreLine{s.start0, dot + 1, s.ident_len - sl - 1});
                             unres.insert(key);
@@ -311,18 +356,31 @@ private:
                     // later rows only matter for the unknown-species warning
                     const char *sp = mem_ + p + 1;
                     while (sp < mem_ + le && *sp == ' ') ++sp;
-                    const char *dot = (const char *)memchr(sp, '.', (size_t)(mem_ + le - sp));
-                    const char *spc = (const char *)memchr(sp, ' ', (size_t)(mem_ + le - sp));
-                    if (dot && (!spc || dot < spc)) {
-                        key.assign(sp, (size_t)(dot - sp));
-                        for (char &ch : key) ch = (char)tolower((unsigned char)ch);
-                        if (!model_.seqid_to_phyloid.count(key)) unres.insert(key);
+                    const char *tok_end = sp;
+                    while (tok_end < mem_ + le && *tok_end != ' ') ++tok_end;
+                    const char *dot = (const char *)memchr(sp, '.', (size_t)(tok_end - sp));
+                    if (dot) {
+                        const int sl = (int)(dot - sp);
+                        const size_t k = cur_lines.size();
+                        bool known;
+                        if (k < prev_lines.size() && prev_lines[k].len == sl && memcmp(prev_lines[k].name, sp, (size_t)sl) == 0) {
+                            known = prev_lines[k].known;
+                        } else {
+                            key.assign(sp, (size_t)sl);
+                            for (char &ch : key) ch = (char)tolower((unsigned char)ch);
+                            known = model_.seqid_to_phyloid.count(key) != 0;
+                            if (!known) unres.insert(key);
+                        }
+                        cur_lines.push_back(Seen{sp, sl, known});
+                    } else {
+                        cur_lines.push_back(Seen{sp, -1, false});
                     }
                 }
                 p = le + 1;
             }
             b.end = std::min(p, size_);
             out.push_back(std::move(b));
+            prev_lines.swap(cur_lines);
             pos = p;
         }
     }

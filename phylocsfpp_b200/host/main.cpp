@@ -400,13 +400,15 @@ int main_build_tracks(int argc, char **argv) {
                             char hdr[512];
                             // power track (build_tracks.hpp:139-158)
                             {
-                                std::string &o = text[0];
+                                TextOut o(text[0]);
                                 const int64_t skip = mod3(3 - aln.start_pos);
                                 if (skip + 2 < L) {
                                     snprintf(hdr, sizeof hdr, "fixedStep chrom=%s start=%" PRId64 " step=3 span=3\n", aln.chrom.c_str(), aln.start_pos + skip);
-                                    o += hdr;
+                                    o.text(hdr);
                                 }
-                                for (int64_t pos = skip; pos + 2 < L; pos += 3) my_format(o, 4, (float)((bl[pos] + bl[pos + 1] + bl[pos + 2]) / 3.0));
+                                o.room((size_t)(L / 3 + 1) * 8);
+                                for (int64_t pos = skip; pos + 2 < L; pos += 3) o.value(4, (float)((bl[pos] + bl[pos + 1] + bl[pos + 2]) / 3.0));
+                                o.finish();
                             }
                             // six raw tracks (build_tracks.hpp:160-216; frame arithmetic of update_seqs, parallel_file_reader.hpp:61-113)
                             if (raw) {
@@ -423,7 +425,8 @@ int main_build_tracks(int argc, char **argv) {
                                         o0 = (L - skip_r) % 3; K = (L - skip_r) / 3;
                                     }
                                     const double *src_scores = fwd ? pl : mi;
-                                    std::string &o = text[1 + k];
+                                    TextOut o(text[1 + k]);
+                                    o.room((size_t)(K + 1) * 8);
                                     int64_t prev = -4;
                                     for (int64_t xx = 0; xx < K; ++xx) {
                                         const int64_t off = o0 + 3 * xx;
@@ -432,11 +435,12 @@ int main_build_tracks(int argc, char **argv) {
                                         const int64_t np = aln.start_pos + off;
                                         if (prev + 3 != np) {
                                             snprintf(hdr, sizeof hdr, "fixedStep chrom=%s start=%" PRId64 " step=3 span=3\n", aln.chrom.c_str(), np);
-                                            o += hdr;
+                                            o.text(hdr);
                                         }
                                         prev = np;
-                                        my_format(o, 3, (float)src_scores[off]);
+                                        o.value(3, (float)src_scores[off]);
                                     }
+                                    o.finish();
                                 }
                             }
                         }
@@ -852,6 +856,49 @@ int main_bigwig_dump(int argc, char **argv) {
     return 0;
 }
 
+
+// Test / tuning hook (no GPU needed): the reader alone — scan + chain cutting + read_chain_into of every chain into a reused matrix,
+// `--threads` workers over the chains; prints seconds and columns/s per phase.
+int main_parse_bench(int argc, char **argv) {
+    const Args a = parse_args(argc, argv, {"threads", "mapping", "species", "repeat"});
+    if (a.pos.size() < 2) die("usage: phylocsf_b200 parse-bench [--threads INT] [--repeat INT] <model> <alignments>...");
+    Model model;
+    load_model(model, a.pos[0], a.str("species"), a.str("mapping"));
+    const int threads = std::max(1, a.integer("threads", 4)), repeat = std::max(1, a.integer("repeat", 1));
+    const int nl = model.nl();
+    for (size_t fi = 1; fi < a.pos.size(); ++fi) {
+        const auto t0 = std::chrono::steady_clock::now();
+        MafFile maf(a.pos[fi], model, true, threads);
+        const double t_scan = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        const std::vector<MafFile::Chain> &chains = maf.chains();
+        int64_t max_cols = 1, total = 0;
+        for (const auto &c : chains) { max_cols = std::max(max_cols, c.ref_cols); total += c.ref_id < 0 ? 0 : c.ref_cols; }
+        for (int rep = 0; rep < repeat; ++rep) {
+            std::atomic<size_t> next{0};
+            std::atomic<int64_t> refused{0};
+            std::vector<double> secs(threads, 0.0);
+            const auto t1 = std::chrono::steady_clock::now();
+            std::vector<std::thread> th;
+            for (int t = 0; t < threads; ++t)
+                th.emplace_back([&, t] {
+                    std::vector<uint8_t> mat((size_t)nl * max_cols);
+                    const auto b0 = std::chrono::steady_clock::now();
+                    for (size_t ci = next++; ci < chains.size(); ci = next++)
+                        if (chains[ci].ref_id >= 0 && maf.read_chain_into(chains[ci], mat.data(), chains[ci].ref_cols, nullptr) < 0) ++refused;
+                    secs[t] = std::chrono::duration<double>(std::chrono::steady_clock::now() - b0).count();
+                });
+            for (auto &x : th) x.join();
+            const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
+            double sum = 0;
+            for (double x : secs) sum += x;
+            printf("{\"file\": \"%s\", \"columns\": %" PRId64 ", \"chains\": %zu, \"threads\": %d, \"scan_seconds\": %.3f, \"parse_wall_seconds\": %.3f, "
+                   "\"parse_core_seconds\": %.3f, \"columns_per_core_second\": %.0f, \"refused_chains\": %" PRId64 "}\n",
+                   a.pos[fi].c_str(), total, chains.size(), threads, t_scan, wall, sum, total / std::max(sum, 1e-9), (int64_t)refused);
+        }
+    }
+    return 0;
+}
+
 // Test hook (no GPU needed): the PhyloCSF-HMM stage alone on existing raw tracks.
 int main_smooth_tracks(int argc, char **argv) {
     const Args a = parse_args(argc, argv, {"genome-length", "coding-exons", "output-phylo", "output-regions", "print-hmm"});
@@ -886,10 +933,13 @@ int main_format_selftest(int argc, char **argv) {
             a.clear(); b.clear();
             my_format(a, dec, v); my_format_printf(b, dec, v);
             if (a != b) { if (bad < 10) printf("mismatch %.9g: '%s' vs '%s'\n", v, a.c_str(), b.c_str()); ++bad; }
+            char buf[64];
+            const size_t nb = (size_t)(my_format_to(buf, dec, v) - buf);          // the route the build-tracks workers take
+            if (nb != b.size() || memcmp(buf, b.data(), nb) != 0) { if (bad < 10) printf("mismatch (my_format_to) %.9g: '%.*s' vs '%s'\n", v, (int)nb, buf, b.c_str()); ++bad; }
         }
     };
     const float special[] = {0.f, -0.f, 0.0625f, 0.1875f, -0.0004f, 0.0005f, 0.00049999f, 1e-30f, -1e-30f, 2.f, 10.f, 0.9995f, 0.99951f, 12345.6789f, -999.9995f,
-                             1e10f, 3.4e38f, 0.3125f, 0.4375f, 24.834f, 3.54f};
+                             1e10f, 3.4e38f, 0.3125f, 0.4375f, 24.834f, 3.54f, 3999999.75f, 4000000.f, 4.1e6f, -4.1e6f, 99.9995f, 100.f, 9.9995f, 999.9995f, 1000.5f};
     for (float v : special) check(v);
     for (long i = 0; i < n; ++i) {
         x ^= x << 13; x ^= x >> 7; x ^= x << 17;
@@ -925,6 +975,7 @@ int main(int argc, char **argv) {
     if (tool == "dump-alignments") return main_dump_alignments(argc, argv);
     if (tool == "format-selftest") return main_format_selftest(argc, argv);
     if (tool == "matrix-to-maf") return main_matrix_to_maf(argc, argv);
+    if (tool == "parse-bench") return main_parse_bench(argc, argv);
     if (tool == "annotate-with-tracks") return main_annotate_with_tracks(argc, argv);
     if (tool == "wig-to-bigwig") return main_wig_to_bigwig(argc, argv);
     if (tool == "bigwig-dump") return main_bigwig_dump(argc, argv);

@@ -4,8 +4,10 @@
 // the given format, trailing zeros are stripped but one decimal is kept ("24.834", "3.54", "2.0", "-0.0").
 #pragma once
 
+#include <emmintrin.h>
 #include <sys/stat.h>
 
+#include <algorithm>
 #include <cctype>
 #include <cstdarg>
 #include <cstdio>
@@ -95,5 +97,61 @@ inline void my_format(std::string &out, int decimals, float d) {
     if (__builtin_signbit(r)) *--p = '-';
     out.append(p, (size_t)(e - p));
 }
+
+// my_format into a caller-provided buffer (at least 48 bytes free); returns the new end.  Same text as my_format: the decimal rounding is
+// done by cvtsd2si (ties to even), digits written without loops for the common sizes.
+inline char *my_format_to(char *p, int decimals, float d) {
+    const double scale = decimals == 3 ? 1000.0 : 10000.0;
+    const double x = (double)d * scale;
+    if (!(__builtin_fabs(x) < 4.0e9)) {          // huge, inf, nan: the general route
+        std::string tmp;
+        my_format(tmp, decimals, d);
+        memcpy(p, tmp.data(), tmp.size());
+        return p + tmp.size();
+    }
+    // cvtsd2si rounds to nearest, ties to even (the default MXCSR mode): the decimal rounding printf applies to the exact binary value
+    const long long ri = _mm_cvtsd_si64(_mm_set_sd(x));
+    const uint32_t q = (uint32_t)(ri < 0 ? -ri : ri);
+    if (__builtin_signbit(x)) *p++ = '-';          // also for values that round to zero: "-0.0", as nearbyint(-0.4) = -0.0 prints
+    const uint32_t iscale = decimals == 3 ? 1000u : 10000u;
+    uint32_t ip = q / iscale, frac = q - ip * iscale;
+    if (ip < 10) {
+        *p++ = (char)('0' + ip);
+    } else if (ip < 100) {
+        *p++ = (char)('0' + ip / 10);
+        *p++ = (char)('0' + ip % 10);
+    } else {
+        char tmp[12];
+        int n = 0;
+        do { tmp[n++] = (char)('0' + ip % 10); ip /= 10; } while (ip);
+        while (n) *p++ = tmp[--n];
+    }
+    *p++ = '.';
+    if (decimals == 3) {
+        const uint32_t d0 = frac / 100, d12 = frac - d0 * 100, d1 = d12 / 10, d2 = d12 - d1 * 10;
+        *p++ = (char)('0' + d0);
+        if (d12) { *p++ = (char)('0' + d1); if (d2) *p++ = (char)('0' + d2); }
+    } else {
+        const uint32_t d0 = frac / 1000, r1 = frac - d0 * 1000, d1 = r1 / 100, r2 = r1 - d1 * 100, d2 = r2 / 10, d3 = r2 - d2 * 10;
+        *p++ = (char)('0' + d0);
+        if (r1) { *p++ = (char)('0' + d1); if (r2) { *p++ = (char)('0' + d2); if (d3) *p++ = (char)('0' + d3); } }
+    }
+    *p++ = '\n';
+    return p;
+}
+
+// Append-only text buffer over a std::string with raw-pointer writes (the wig text of a chain: millions of short lines).
+struct TextOut {
+    std::string &s;
+    size_t n;
+    explicit TextOut(std::string &str) : s(str), n(str.size()) {}
+    inline char *room(size_t want) {          // pointer to at least `want` writable bytes at the end
+        if (n + want > s.size()) s.resize(std::max(s.size() * 2, n + want + 4096));
+        return &s[n];
+    }
+    inline void value(int decimals, float d) { char *p = room(48); n = (size_t)(my_format_to(p, decimals, d) - s.data()); }
+    inline void text(const char *t) { const size_t l = strlen(t); memcpy(room(l), t, l); n += l; }
+    void finish() { s.resize(n); }
+};
 
 }  // namespace host

@@ -234,6 +234,7 @@ def leg_config4(total_cols, rank, world, local_rank, dist, torch, capi, precisio
     if world > 1:
         dist.barrier()
     buf = OrderedHostBuffer(path, 3, total_cols)
+    buf.prefault(lo, hi)          # the output array exists and is mapped before the clock starts, like the pinned input / output buffers
     lib = capi.load()
     st = capi.TracksStats()
     flags = capi.TRACKS_SCORES | capi.TRACKS_BLS | precision_flag

@@ -13,6 +13,7 @@
 #include <cinttypes>
 #include <chrono>
 #include <condition_variable>
+#include <functional>
 #include <cmath>
 
 #include "annotate.hpp"
@@ -83,22 +84,30 @@ struct OrderedSink {
 };
 
 // Device models are pooled: two per GPU (one call can copy while the other computes); more host threads inside the library
-// would only contend for the device and the driver.
+// would only contend for the device and the driver.  ONE pool over all GPUs, dealt dynamically like the reference's
+// `schedule(dynamic, 1)` jobs (build_tracks.hpp:88): a worker takes whichever model is free, on the GPU with the fewest calls in
+// flight.  Models join the pool as soon as they exist, so the first groups are scored while the CUDA contexts of the other devices
+// are still coming up (eight contexts take ~1.5 s); the output does not depend on who scored what.
 struct ModelPool {
     std::mutex mu;
     std::condition_variable cv;
-    std::vector<pcsf_model *> free_models;
-    std::vector<pcsf_model *> all;
-    void add(pcsf_model *m) { free_models.push_back(m); all.push_back(m); }
-    pcsf_model *acquire() {
+    struct Entry { pcsf_model *m; int dev; };
+    std::vector<Entry> free_models, all;
+    std::vector<int> busy;          // calls in flight per GPU
+    explicit ModelPool(int gpus) : busy(gpus, 0) {}
+    void add(pcsf_model *m, int dev) { { std::lock_guard<std::mutex> g(mu); free_models.push_back({m, dev}); all.push_back({m, dev}); } cv.notify_all(); }
+    Entry acquire() {
         std::unique_lock<std::mutex> g(mu);
         cv.wait(g, [&] { return !free_models.empty(); });
-        pcsf_model *m = free_models.back();
-        free_models.pop_back();
-        return m;
+        size_t best = 0;
+        for (size_t i = 1; i < free_models.size(); ++i) if (busy[free_models[i].dev] < busy[free_models[best].dev]) best = i;
+        const Entry e = free_models[best];
+        free_models.erase(free_models.begin() + (long)best);
+        ++busy[e.dev];
+        return e;
     }
-    void release(pcsf_model *m) { { std::lock_guard<std::mutex> g(mu); free_models.push_back(m); } cv.notify_one(); }
-    void destroy() { for (pcsf_model *m : all) pcsf_model_destroy(m); all.clear(); free_models.clear(); }
+    void release(const Entry &e) { { std::lock_guard<std::mutex> g(mu); free_models.push_back(e); --busy[e.dev]; } cv.notify_one(); }
+    void destroy() { for (const Entry &e : all) pcsf_model_destroy(e.m); all.clear(); free_models.clear(); }
 };
 
 // Page-locked host buffer that only grows (25 % headroom): the matrices and score vectors of a worker thread are handed to
@@ -126,16 +135,19 @@ struct PinnedBuf {
 
 int default_gpus() { return std::max(1, pcsf_device_count()); }
 
-// one pool per GPU, filled in parallel (model preparation is host work: eigensystem + all P(t) + uploads)
-void make_pools(const Model &model, int gpus, int per_gpu, std::vector<std::unique_ptr<ModelPool>> &pools) {
-    std::vector<pcsf_model *> ms((size_t)gpus * per_gpu);
+// One thread per GPU prepares that GPU's models one after the other (host work: eigensystem, all P(t), tables; then the uploads) and
+// hands each to the pool as soon as it exists; `stop` (all groups scored) skips models nobody will need any more.
+void fill_pool(const Model &model, int gpus, int per_gpu, ModelPool &pool, const std::atomic<bool> &stop, const std::function<void(pcsf_model *)> &configure) {
     std::vector<std::thread> th;
-    for (size_t i = 0; i < ms.size(); ++i) th.emplace_back([&, i] { ms[i] = create_device_model(model, (int)(i / per_gpu)); });
+    for (int g = 0; g < gpus; ++g)
+        th.emplace_back([&, g] {
+            for (int k = 0; k < per_gpu && !stop; ++k) {
+                pcsf_model *m = create_device_model(model, g);
+                configure(m);
+                pool.add(m, g);
+            }
+        });
     for (auto &t : th) t.join();
-    for (int g = 0; g < gpus; ++g) {
-        pools.emplace_back(new ModelPool);
-        for (int k = 0; k < per_gpu; ++k) pools.back()->add(ms[(size_t)g * per_gpu + k]);
-    }
 }
 
 void warn_unresolved(const MafFile &maf) {
@@ -192,12 +204,21 @@ int main_build_tracks(int argc, char **argv) {
     // Start-up overlaps three things: the device models (CUDA context + eigensystems + uploads, two per GPU) are prepared by their own
     // threads while the input files are scanned and cut into chains, and while the page-locked staging slab is allocated.
     const auto t_start = std::chrono::steady_clock::now();
-    std::vector<std::unique_ptr<ModelPool>> pools;
+    ModelPool pool(gpus);
+    std::atomic<bool> stop_models{false};
     const int per_gpu = getenv("PCSF_HOST_MODELS_PER_GPU") ? std::max(1, atoi(getenv("PCSF_HOST_MODELS_PER_GPU"))) : 2;
-    std::thread pool_maker([&] { make_pools(model, gpus, per_gpu, pools); });
+    const bool dev_timing = getenv("PCSF_HOST_TIMING") != nullptr;          // per-stage CUDA-event times of every library call (diagnostic)
+    std::atomic<double> t_first_model{0.0};
+    std::thread pool_maker([&] {
+        fill_pool(model, gpus, per_gpu, pool, stop_models, [&](pcsf_model *dm) {
+            if (dev_timing) pcsf_set_timing(dm, 1);
+            if (getenv("PCSF_HOST_CHUNK_COLS")) pcsf_set_chunk_columns(dm, atoll(getenv("PCSF_HOST_CHUNK_COLS")));
+            double expect = 0.0;
+            t_first_model.compare_exchange_strong(expect, std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());
+        });
+    });
     std::vector<std::vector<uint8_t>> seen(threads, std::vector<uint8_t>(nl, 0));
     double t_parse = 0.0, t_format = 0.0, t_scan = 0.0, t_wait_model = 0.0, t_wait_writer = 0.0;
-    const bool dev_timing = getenv("PCSF_HOST_TIMING") != nullptr;          // per-stage CUDA-event times of every library call (diagnostic)
     double dev_ms[6] = {0, 0, 0, 0, 0, 0};
     int64_t dev_unique = 0, dev_windows = 0;
     static const char *kFrames[6] = {"+1", "+2", "+3", "-1", "-2", "-3"};
@@ -261,19 +282,12 @@ int main_build_tracks(int argc, char **argv) {
     std::vector<uint8_t *> slabs(slab_threads, nullptr);
     for (auto &p : slabs)
         if (posix_memalign(reinterpret_cast<void **>(&p), 4096, per_thread) != 0) die("cannot allocate %zu bytes of staging memory", per_thread);
-    std::mutex ready_mu;
-    std::condition_variable ready_cv;
-    bool pools_ready = false;
     std::atomic<bool> stop_pinning{false};
     std::vector<char> pinned(slab_threads, 0);
     double t_slab = 0.0, t_startup = 0.0;
     std::thread pool_waiter([&] {
         pool_maker.join();
-        if (dev_timing) for (auto &p : pools) for (pcsf_model *dm : p->all) pcsf_set_timing(dm, 1);
-        if (getenv("PCSF_HOST_CHUNK_COLS")) for (auto &p : pools) for (pcsf_model *dm : p->all) pcsf_set_chunk_columns(dm, atoll(getenv("PCSF_HOST_CHUNK_COLS")));
         t_startup = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
-        { std::lock_guard<std::mutex> g(ready_mu); pools_ready = true; }
-        ready_cv.notify_all();
         // Pinning pays only on long runs: ~1 s per GB during which the library calls of the other threads crawl (measured: 100 M
         // columns take 1.9 s unpinned, 2.5-3.0 s with any pinning scheme), against 0.4 s saved per 100 M columns once pinned.
         const char *pin_env = getenv("PCSF_HOST_PINNING");
@@ -287,7 +301,7 @@ int main_build_tracks(int argc, char **argv) {
     sink.resize(total_chains);
     std::atomic<size_t> next{0};
     std::atomic<int64_t> cols{0};
-    std::vector<std::atomic<int64_t>> gpu_cols(gpus);          // reference columns scored per device (the deal is group gi -> GPU gi mod gpus)
+    std::vector<std::atomic<int64_t>> gpu_cols(gpus);          // reference columns scored per device (dynamic deal: whichever device has a free model)
     for (auto &g : gpu_cols) g = 0;
     std::mutex gpu_time_mu;
     // back-pressure: the workers run at most this many reference columns ahead of the writer (their finished text waits in memory,
@@ -302,7 +316,6 @@ int main_build_tracks(int argc, char **argv) {
                 if (t >= slab_threads) return;          // fewer groups than threads
                 std::vector<Alignment> alns;
                 uint8_t *const my_slab = slabs[t];
-                bool have_pools = false;
                 std::vector<uint8_t> fallback_mat;          // only for a group whose text disagrees with its size fields
                 std::vector<double> fallback_out;
                 const uint8_t *src = nullptr;
@@ -366,13 +379,8 @@ int main_build_tracks(int argc, char **argv) {
                         }
                         const auto p1 = now();
                         my_parse += secs(p0, p1);
-                        if (!have_pools) {
-                            std::unique_lock<std::mutex> g(ready_mu);
-                            ready_cv.wait(g, [&] { return pools_ready; });
-                            have_pools = true;
-                        }
-                        ModelPool &pool = *pools[gi % gpus];
-                        pcsf_model *dm = pool.acquire();
+                        const ModelPool::Entry me = pool.acquire();
+                        pcsf_model *dm = me.m;
                         const auto g0 = now();
                         my_wait_model += secs(p1, g0);
                         pcsf_tracks_stats cs{};
@@ -384,11 +392,11 @@ int main_build_tracks(int argc, char **argv) {
                             dev_ms[0] += cs.ms_pack; dev_ms[1] += cs.ms_hash; dev_ms[2] += cs.ms_dedup; dev_ms[3] += cs.ms_prune; dev_ms[4] += cs.ms_scatter;
                             dev_ms[5] += cs.ms_bls; dev_unique += cs.n_unique; dev_windows += cs.n_windows;
                         }
-                        pool.release(dm);
+                        pool.release(me);
                         if (st == PCSF_ERR_BAD_CHAR) { fprintf(stderr, "%s\n", pcsf_last_error()); exit(37); }      // translation.hpp:46-51
                         if (st != PCSF_OK) die("pcsf_tracks: %s", pcsf_last_error());
                         cols += Ltot;
-                        gpu_cols[gi % gpus] += Ltot;
+                        gpu_cols[me.dev] += Ltot;
                     }
                     const auto f0 = now();
                     for (size_t ci = c0; ci < c1; ++ci) {
@@ -497,6 +505,7 @@ int main_build_tracks(int argc, char **argv) {
     }
     for (auto &w : workers) w.join();
     stop_pinning = true;
+    stop_models = true;
     pool_waiter.join();
     total_cols += cols;
     if (to_bigwig) {
@@ -523,9 +532,9 @@ int main_build_tracks(int argc, char **argv) {
         std::string per_gpu;
         for (int g = 0; g < gpus; ++g) per_gpu += (g ? ", " : "") + std::to_string((long long)gpu_cols[g]);
         printf("{\"columns\": %" PRId64 ", \"seconds\": %.3f, \"columns_per_s\": %.1f, \"threads\": %d, \"gpus\": %d, \"scan_seconds\": %.3f, "
-               "\"startup_seconds\": %.3f, \"parse_seconds_sum\": %.3f, \"pinned_alloc_seconds\": %.3f, \"wait_model_seconds_sum\": %.3f, \"wait_writer_seconds_sum\": %.3f, "
+               "\"first_model_seconds\": %.3f, \"startup_seconds\": %.3f, \"parse_seconds_sum\": %.3f, \"pinned_alloc_seconds\": %.3f, \"wait_model_seconds_sum\": %.3f, \"wait_writer_seconds_sum\": %.3f, "
                "\"gpu_call_seconds_sum\": %.3f, \"format_seconds_sum\": %.3f, \"columns_per_gpu\": [%s]}\n",
-               total_cols, wall, total_cols / wall, threads, gpus, t_scan, t_startup, t_parse, t_slab, t_wait_model, t_wait_writer, t_gpu, t_format, per_gpu.c_str());
+               total_cols, wall, total_cols / wall, threads, gpus, t_scan, t_first_model.load(), t_startup, t_parse, t_slab, t_wait_model, t_wait_writer, t_gpu, t_format, per_gpu.c_str());
     }
     if (dev_timing)
         printf("{\"ms_pack\": %.2f, \"ms_hash\": %.2f, \"ms_dedup\": %.2f, \"ms_prune\": %.2f, \"ms_scatter\": %.2f, \"ms_bls\": %.2f, \"windows\": %" PRId64
@@ -536,10 +545,18 @@ int main_build_tracks(int argc, char **argv) {
         for (int t = 0; t < threads; ++t) any |= seen[t][s] != 0;
         if (!any) printf("\033[33mWARNING: species %s from the model was never seen in any alignment.\033[0m\n", model.tree.labels[s].c_str());
     }
+    // Everything is on disk.  Tearing down the device models, the staging memory and up to eight CUDA contexts in an orderly fashion
+    // costs 0.3-2 s that nobody waits for; the operating system reclaims all of it (PCSF_HOST_ORDERLY_EXIT=1 keeps the teardown, e.g.
+    // under compute-sanitizer).
+    if (!getenv("PCSF_HOST_ORDERLY_EXIT")) {
+        fflush(stdout);
+        fflush(stderr);
+        _exit(0);
+    }
     const auto x0 = std::chrono::steady_clock::now();
     for (int t = 0; t < slab_threads; ++t) { if (pinned[t]) pcsf_unregister_host(slabs[t]); free(slabs[t]); }
     const auto x1 = std::chrono::steady_clock::now();
-    for (auto &p : pools) p->destroy();
+    pool.destroy();
     const auto x2 = std::chrono::steady_clock::now();
     fctx.clear();
     const auto x3 = std::chrono::steady_clock::now();

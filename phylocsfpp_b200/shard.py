@@ -64,9 +64,21 @@ class OrderedHostBuffer:
         self.dtype = np.dtype(dtype)
         nbytes = rows * total * self.dtype.itemsize
         if create:
+            import os
             with open(path, "wb") as fh:
                 fh.truncate(nbytes)
+                if nbytes:
+                    try:
+                        os.posix_fallocate(fh.fileno(), 0, nbytes)          # the pages exist before anybody writes (tmpfs: no allocation faults later)
+                    except OSError:
+                        pass
         self.arr = np.memmap(path, dtype=self.dtype, mode="r+", shape=(rows, total))
+
+    def prefault(self, col0: int, col1: int) -> None:
+        """Touches this rank's column range once (page-table entries of the shared mapping), as one would for any output buffer."""
+        if col1 > col0:
+            step = max(1, 4096 // self.dtype.itemsize)
+            self.arr[:, col0:col1:step] = 0          # a write, so that the pages are mapped writable (the file is all zeros anyway)
 
     @staticmethod
     def pick_dir(nbytes: int) -> str:

@@ -136,16 +136,29 @@ struct PinnedBuf {
 int default_gpus() { return std::max(1, pcsf_device_count()); }
 
 // One thread per GPU prepares that GPU's models one after the other (host work: eigensystem, all P(t), tables; then the uploads) and
-// hands each to the pool as soon as it exists; `stop` (all groups scored) skips models nobody will need any more.
+// hands each to the pool as soon as it exists; `stop` (all groups scored) skips models nobody will need any more.  CUDA contexts are
+// brought up two devices at a time (GPU g waits for the first model of GPU g-2): eight contexts created at once all become usable
+// together after ~1.5 s (measured: first model after 0.30-0.43 s with one or two devices, 1.45 s with eight), staggered the first
+// two devices score while the others are still coming up.
 void fill_pool(const Model &model, int gpus, int per_gpu, ModelPool &pool, const std::atomic<bool> &stop, const std::function<void(pcsf_model *)> &configure) {
     std::vector<std::thread> th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<char> up(gpus, 0);          // GPU g has its first model (or gave up)
     for (int g = 0; g < gpus; ++g)
         th.emplace_back([&, g] {
+            if (g >= 2) {
+                std::unique_lock<std::mutex> l(mu);
+                cv.wait(l, [&] { return up[g - 2] != 0; });
+            }
             for (int k = 0; k < per_gpu && !stop; ++k) {
                 pcsf_model *m = create_device_model(model, g);
                 configure(m);
                 pool.add(m, g);
+                if (k == 0) { { std::lock_guard<std::mutex> l(mu); up[g] = 1; } cv.notify_all(); }
             }
+            { std::lock_guard<std::mutex> l(mu); up[g] = 1; }
+            cv.notify_all();
         });
     for (auto &t : th) t.join();
 }

@@ -90,6 +90,74 @@ def test_reader_synthetic_breakpoints_holes_gaps(tmp_path):
     _compare(rows[:2000], ref[:2000])
 
 
+def test_reader_odd_line_formats(tmp_path):
+    """The fast line path of read_chain_into (species + text taken without tokenising the fields in between; species of line k
+    compared with line k of the previous block) against the full tokeniser and the Python mirror on lines a strtok reader accepts
+    but a careless one trips over: runs of spaces between fields, trailing spaces, an eighth token, a longer first
+    token, `i` / `e` / `q` lines, species order changing from block to block, upper-case species, bare `a` lines."""
+    _need_bin()
+    import random
+    from make_synth_maf import write_synth_maf
+    model = load_model("12flies")
+    plain = os.path.join(str(tmp_path), "plain.maf")
+    write_synth_maf(plain, model, 60_000, seed=11, hole_p=1 / 2000.0)
+    rnd = random.Random(3)
+    out = []
+    block = []
+
+    def flush():
+        if block:
+            head, rows = block[0], block[1:]
+            if len(rows) > 2 and rnd.random() < 0.3:          # species order changes (the reference row stays first)
+                first, rest = rows[0], rows[1:]
+                rnd.shuffle(rest)
+                rows = [first] + rest
+            out.append(head)
+            out.extend(rows)
+            block.clear()
+    for ln in open(plain).read().split("\n"):
+        if ln.startswith("a"):
+            flush()
+            block.append("a" if rnd.random() < 0.2 else ln)
+        elif ln.startswith("s "):
+            tok = ln.split()
+            k = rnd.random()
+            if k < 0.15:
+                ln = "s  " + tok[1] + "   " + "  ".join(tok[2:6]) + "    " + tok[6]          # runs of spaces
+            elif k < 0.30:
+                ln = ln + "  "                                                               # trailing spaces
+            elif k < 0.45:
+                ln = tok[0] + " " + tok[1] + " " + " ".join(tok[2:6]) + " " + tok[6] + " "   # single trailing space
+            elif k < 0.55:
+                ln = ln + " extra"                                                           # an eighth token (ignored by strtok readers)
+            elif k < 0.60:
+                ln = "sx" + ln[1:]                                                           # first token longer than one character
+            elif k < 0.70:
+                sp, rest = tok[1].split(".", 1)
+                ln = " ".join([tok[0], sp.upper() + "." + rest] + tok[2:])                  # upper-case species
+            block.append(ln)
+            if rnd.random() < 0.1:
+                block.append("i " + tok[1] + " C 0 C 0")
+            if rnd.random() < 0.05:
+                block.append("q " + tok[1] + " " + "9" * len(tok[6]))
+        elif ln == "":
+            flush()
+            out.append("")
+        else:
+            flush()
+            out.append(ln)
+    flush()
+    odd = os.path.join(str(tmp_path), "odd.maf")
+    open(odd, "w").write("\n".join(out) + "\n")
+    ref = list(MafReader(odd, model.seqid_to_phyloid, model.nl, True, warn=False))
+    base = list(MafReader(plain, model.seqid_to_phyloid, model.nl, True, warn=False))
+    assert len(ref) == len(base) and all(a.L == b.L and np.array_equal(a.seqs, b.seqs) for a, b in zip(ref, base))
+    for threads in (1, 4):          # dump-alignments itself dies if read_chain_into and read_chain disagree on a chain
+        _compare(_dump("12flies", odd, True, threads), ref, hash_limit=10 ** 7)
+    env = dict(os.environ, PCSF_REQUIRE_DIRECT="1")          # and none of these lines may push a chain onto the slow path
+    subprocess.run([BIN, "dump-alignments", "--hash", "0", "--threads", "2", "12flies", odd], check=True, capture_output=True, env=env)
+
+
 def test_wig_number_formatting_matches_printf():
     """my_fprintf (reference src/common.hpp:48-68) re-implemented without snprintf: identical text on 2 M pseudo-random
     floats, exact rounding ties and special values."""

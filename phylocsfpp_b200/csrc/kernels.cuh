@@ -516,6 +516,9 @@ __global__ void __launch_bounds__(PR_THREADS, 1) k_prune(const PruneArgs a) {
         // warp's non-DMMA phase overlap the other's DMMA phase.
         if (warp >= PR_NWARP / 2 && a.stagger_ns) __nanosleep(a.stagger_ns);
 
+        // score-msa tiles belong to one alignment each and are rarely full (config 5: 68 % of the warps have windows): a warp without
+        // windows only keeps the tile ring's barriers in step, its SMSP's DMMA pipe is left to the warp it shares it with
+        const bool idle_warp = PER_TILE && (uint32_t)(warp * 8) >= td.count;
         for (int mm = 0; mm < NMODEL; ++mm) {
             const int m = PER_TILE ? td.model : mm;
             const double *leafPT = PER_TILE ? td.leafPT : a.leafPT[m];
@@ -523,6 +526,17 @@ __global__ void __launch_bounds__(PR_THREADS, 1) k_prune(const PruneArgs a) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) R[i] = 0.0;
             int sp = 0;
+            if (idle_warp) {
+                for (int pc = 0; pc < a.n_ops; ++pc) {
+                    if ((prog[pc] >> 16) != OP_GEMM) continue;
+                    const uint32_t st = use % PR_NSTAGE;
+                    mbar_wait(full + st, (use / PR_NSTAGE) & 1);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty + st);
+                    ++use;
+                }
+                continue;
+            }
             for (int pc = 0; pc < a.n_ops; ++pc) {
                 const int32_t op = prog[pc];
                 const int code = op >> 16, arg = op & 0xffff;

@@ -352,17 +352,7 @@ __global__ void __launch_bounds__(128) k_mle_expm(const MleSlot *__restrict__ sl
             rowsum += acc[mt][c];
         }
         rowsum += __shfl_xor_sync(0xffffffffu, rowsum, 1); rowsum += __shfl_xor_sync(0xffffffffu, rowsum, 2);
-        if (gi >= 0) {
-            // fragment order: tile[ks][ntp][lane][e] = P[a][bb], a = 8(2ntp+e)+lane/4, bb = 8(ks/2)+2(lane%4)+ks%2
-            double *tile = slot_base + (size_t)gi * 4096;
-            const int ntp = (i >> 3) >> 1, e = (i >> 3) & 1, lhi = i & 7;
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                const int j = 8 * (c >> 1) + 2 * q + (c & 1);
-                const int ks = 2 * (j >> 3) + (j & 1), llo = (j & 7) >> 1;
-                tile[((ks * 4 + ntp) * 32 + 4 * lhi + llo) * 2 + e] = acc[mt][c];
-            }
-        } else {
+        if (gi < 0) {
             // leaf table: pt[x][a] = P[a][x]; pt[64][a] = row sum
             double *pt = slot_base + leaf_off + (size_t)b * 65 * 64;
 #pragma unroll
@@ -372,6 +362,14 @@ __global__ void __launch_bounds__(128) k_mle_expm(const MleSlot *__restrict__ sl
             }
             if (q == 0) pt[64 * 64 + i] = rowsum;
         }
+    }
+    if (gi >= 0) {
+        // fragment order: tile[ks][ntp][lane][e] = P[a][bb], a = 8(2ntp+e)+lane/4, bb = 8(ks/2)+2(lane%4)+ks%2.  For this thread's rows
+        // (row0 + g and row0 + 8 + g) that is ntp = warp, e = mt, lane = 4g + q = its own lane, ks = c: the two rows of column c are the
+        // two halves of ONE 16-byte slot, so a warp writes 512 contiguous bytes per c
+        double2 *tile = reinterpret_cast<double2 *>(slot_base + (size_t)gi * 4096);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) tile[(c * 4 + warp) * 32 + lane] = make_double2(acc[0][c], acc[1][c]);
     }
     if (bad) atomicOr(expm_err + si, 1);
 }

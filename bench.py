@@ -466,6 +466,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-port", action="store_true", help="time the oracle port instead of the reference binary on the CPU legs")
     ap.add_argument("--no-dedup", action="store_true")
+    ap.add_argument("--chunk-cols", type=int, default=0, help="dedup / pipeline chunk of the library in columns (0 = the library's default, 2 Mi)")
     ap.add_argument("--config4-cols", type=int, default=250_000_000, help="columns of the strong-scaled 100vertebrates leg (0 = skip)")
     ap.add_argument("--config5-alignments", type=int, default=1_000_000, help="alignments of the strong-scaled MLE leg (0 = skip)")
     ap.add_argument("--cli-cols", type=int, default=100_000_000, help="columns of the MAF files of the command-line leg, four chromosome files (0 = skip)")
@@ -552,6 +553,8 @@ def main():
     B = args.cols
     Wn = B - 2
     dm = capi.DeviceModel(model, local_rank)
+    if args.chunk_cols:
+        dm.set_chunk_columns(args.chunk_cols)
     seqs = synth_alignment(model, B, seed=1234 + rank, device=dev)     # [nl, ld] resident in HBM
     ld = seqs.shape[1]
     plus = torch.empty(Wn, dtype=torch.float64, device=dev)

@@ -128,7 +128,7 @@ pcsf_status pcsf_tracks_device(pcsf_model *m, const uint8_t *d_seqs, int64_t L, 
 /* Synchronises the stream, checks the bad-character flag and fills stats. */
 pcsf_status pcsf_tracks_device_finish(pcsf_model *m, void *cuda_stream, pcsf_tracks_stats *stats);
 
-/* Maximum number of columns per dedup chunk (default 1<<22); 0 restores the default. */
+/* Maximum number of columns per dedup chunk (default 1<<21); 0 restores the default. */
 pcsf_status pcsf_set_chunk_columns(pcsf_model *m, int64_t columns);
 /* Enable/disable per-stage CUDA-event timing in pcsf_tracks (adds synchronisation). */
 pcsf_status pcsf_set_timing(pcsf_model *m, int enabled);

@@ -96,7 +96,7 @@ struct pcsf_model {
     DevBuf codes, klo, khi, slot, flag, uniq, pidx, table, slotmin, bsums, logz, anc, misc, io_in, io_out, perwin, mle;
     int *d_bad = nullptr;
     uint32_t *d_nuniq = nullptr;       // [max chunks]
-    int64_t chunk_cols = (int64_t)1 << 22;
+    int64_t chunk_cols = (int64_t)1 << 21;          // 2 Mi columns: calls of 4 Mi columns and more are pipelined (H2D | compute | D2H per chunk)
     bool timing = false;
     uint32_t stagger_ns = 1000;
     pcsf_tracks_stats last{};
@@ -266,7 +266,7 @@ extern "C" pcsf_status pcsf_model_get(const pcsf_model *m, int which, double *la
 
 extern "C" pcsf_status pcsf_set_chunk_columns(pcsf_model *m, int64_t columns) {
     if (!m || columns < 0) return fail(PCSF_ERR_INVALID, "pcsf_set_chunk_columns: bad argument");
-    if (columns == 0) columns = (int64_t)1 << 22;
+    if (columns == 0) columns = (int64_t)1 << 21;
     if (columns > ((int64_t)1 << 23)) columns = (int64_t)1 << 23;   // window ids are 32-bit, scan is 2-level
     m->chunk_cols = columns;
     return PCSF_OK;

@@ -139,19 +139,23 @@ int default_gpus() { return std::max(1, pcsf_device_count()); }
 // hands each to the pool as soon as it exists; `stop` (all groups scored) skips models nobody will need any more.  CUDA contexts are
 // brought up two devices at a time (GPU g waits for the first model of GPU g-2): eight contexts created at once all become usable
 // together after ~1.5 s (measured: first model after 0.30-0.43 s with one or two devices, 1.45 s with eight), staggered the first
-// two devices score while the others are still coming up.
-void fill_pool(const Model &model, int gpus, int per_gpu, ModelPool &pool, const std::atomic<bool> &stop, const std::function<void(pcsf_model *)> &configure) {
+// two devices score while the others are still coming up.  `allowed` is how many devices the job is worth (set after the scan, see
+// the caller): devices beyond it are never initialised.
+void fill_pool(const Model &model, int gpus, int per_gpu, ModelPool &pool, const std::atomic<bool> &stop, const std::atomic<int> &allowed,
+               const std::function<void(pcsf_model *)> &configure) {
     std::vector<std::thread> th;
     std::mutex mu;
     std::condition_variable cv;
     std::vector<char> up(gpus, 0);          // GPU g has its first model (or gave up)
     for (int g = 0; g < gpus; ++g)
         th.emplace_back([&, g] {
-            if (g >= 2) {
+            {
                 std::unique_lock<std::mutex> l(mu);
-                cv.wait(l, [&] { return up[g - 2] != 0; });
+                // `allowed` changes once (0 = not decided yet for g >= 2) and `stop` once: poll them with a short timeout
+                while (!stop && !((g < 2 || up[g - 2] != 0) && (g < 2 || allowed.load() != 0))) cv.wait_for(l, std::chrono::milliseconds(2));
             }
-            for (int k = 0; k < per_gpu && !stop; ++k) {
+            const int lim = allowed.load() == 0 ? std::min(gpus, 2) : allowed.load();
+            for (int k = 0; k < per_gpu && !stop && g < lim; ++k) {
                 pcsf_model *m = create_device_model(model, g);
                 configure(m);
                 pool.add(m, g);
@@ -219,11 +223,12 @@ int main_build_tracks(int argc, char **argv) {
     const auto t_start = std::chrono::steady_clock::now();
     ModelPool pool(gpus);
     std::atomic<bool> stop_models{false};
+    std::atomic<int> allowed_gpus{0};          // decided after the scan: how many devices this input is worth
     const int per_gpu = getenv("PCSF_HOST_MODELS_PER_GPU") ? std::max(1, atoi(getenv("PCSF_HOST_MODELS_PER_GPU"))) : 2;
     const bool dev_timing = getenv("PCSF_HOST_TIMING") != nullptr;          // per-stage CUDA-event times of every library call (diagnostic)
     std::atomic<double> t_first_model{0.0};
     std::thread pool_maker([&] {
-        fill_pool(model, gpus, per_gpu, pool, stop_models, [&](pcsf_model *dm) {
+        fill_pool(model, gpus, per_gpu, pool, stop_models, allowed_gpus, [&](pcsf_model *dm) {
             if (dev_timing) pcsf_set_timing(dm, 1);
             if (getenv("PCSF_HOST_CHUNK_COLS")) pcsf_set_chunk_columns(dm, atoll(getenv("PCSF_HOST_CHUNK_COLS")));
             double expect = 0.0;
@@ -278,6 +283,11 @@ int main_build_tracks(int argc, char **argv) {
         total_chains += chains.size();
         fctx.push_back(std::move(fc));
     }
+    // How many devices is this input worth?  Bringing a device up costs ~0.4 s during which the calls on the devices already working
+    // slow down (measured on the 8-GPU box: 100 M columns take 1.22 s on two devices, 2.2 s when eight are brought up), and a device
+    // scores ~60-100 M columns/s through this host: one device per 60 M columns (PCSF_HOST_USE_ALL_GPUS=1: all of --gpus).
+    const int gpus_worth = getenv("PCSF_HOST_USE_ALL_GPUS") ? gpus : (int)std::min<int64_t>(gpus, std::max<int64_t>(1, (cols_before + 30000000) / 60000000));
+    allowed_gpus = gpus_worth;
     // Staging, one region per worker, sized by the largest group (known exactly from the scan).  Pinning runs at 1-2 GB/s and competes
     // with the model preparation for the driver, so the regions are plain page-aligned memory that the workers parse into from the
     // first millisecond; once the models are up a background thread page-locks them in place, one after the other
@@ -544,10 +554,10 @@ int main_build_tracks(int argc, char **argv) {
     if (getenv("PCSF_HOST_STATS")) {
         std::string per_gpu;
         for (int g = 0; g < gpus; ++g) per_gpu += (g ? ", " : "") + std::to_string((long long)gpu_cols[g]);
-        printf("{\"columns\": %" PRId64 ", \"seconds\": %.3f, \"columns_per_s\": %.1f, \"threads\": %d, \"gpus\": %d, \"scan_seconds\": %.3f, "
+        printf("{\"columns\": %" PRId64 ", \"seconds\": %.3f, \"columns_per_s\": %.1f, \"threads\": %d, \"gpus\": %d, \"gpus_worth\": %d, \"scan_seconds\": %.3f, "
                "\"first_model_seconds\": %.3f, \"startup_seconds\": %.3f, \"parse_seconds_sum\": %.3f, \"pinned_alloc_seconds\": %.3f, \"wait_model_seconds_sum\": %.3f, \"wait_writer_seconds_sum\": %.3f, "
                "\"gpu_call_seconds_sum\": %.3f, \"format_seconds_sum\": %.3f, \"columns_per_gpu\": [%s]}\n",
-               total_cols, wall, total_cols / wall, threads, gpus, t_scan, t_first_model.load(), t_startup, t_parse, t_slab, t_wait_model, t_wait_writer, t_gpu, t_format, per_gpu.c_str());
+               total_cols, wall, total_cols / wall, threads, gpus, gpus_worth, t_scan, t_first_model.load(), t_startup, t_parse, t_slab, t_wait_model, t_wait_writer, t_gpu, t_format, per_gpu.c_str());
     }
     if (dev_timing)
         printf("{\"ms_pack\": %.2f, \"ms_hash\": %.2f, \"ms_dedup\": %.2f, \"ms_prune\": %.2f, \"ms_scatter\": %.2f, \"ms_bls\": %.2f, \"windows\": %" PRId64

@@ -351,7 +351,8 @@ def test_build_tracks_cli_sharded_over_gpus(tmp_path):
     from phylocsfpp_b200.models import load_model
     maf = os.path.join(str(tmp_path), "shard.maf")
     write_synth_maf(maf, load_model("58mammals"), 400000, seed=77, mean_block=150, hole_p=1 / 60.0, ref_gap=0.01, alien_p=0.02, start0=800000)
-    env = dict(os.environ, PCSF_HOST_GROUP_COLS="30000", PCSF_HOST_STATS="1")
+    # small groups so that there is something to deal; PCSF_HOST_USE_ALL_GPUS: the host would not bring a second device up for 400 k columns
+    env = dict(os.environ, PCSF_HOST_GROUP_COLS="30000", PCSF_HOST_STATS="1", PCSF_HOST_USE_ALL_GPUS="1")
     for prec in ("f64", "tc5"):
         outs = []
         for g in (1, 2):

@@ -343,7 +343,7 @@ static pcsf_status dedup_and_prune(pcsf_model *m, const WinSpace &ws, uint32_t n
         const uint32_t mp = (nwin + 255) / 256;
         CK(m->tc5_ids.reserve((size_t)mp * 2 * m->host.nl * 128));
         m->launches++;
-        k_tc5_ids<<<std::min<uint32_t>(mp, (uint32_t)m->sm_count * 8), 256, 0, st>>>(ws, m->uniq.as<uint32_t>(), d_nuniq_slot, m->tc5_ids.as<uint8_t>());
+        k_tc5_ids<<<std::min<uint32_t>(mp, (uint32_t)m->sm_count * 16), 128, 0, st>>>(ws, m->uniq.as<uint32_t>(), d_nuniq_slot, m->tc5_ids.as<uint8_t>());
         CK(cudaGetLastError());
         PruneTc5Args ta{};
         ta.ids = m->tc5_ids.as<uint8_t>();

@@ -92,29 +92,53 @@ inline void prune_tc5_pick_stages(int nl, int n_steps, int n_src, int *nstage, i
 
 // Codon ids of the unique windows in the layout the producers of k_prune_tc5 read: block (pair, chain) = [leaf][128 windows].
 // Windows past n_unique repeat the last one (their results are never stored).
-__global__ void __launch_bounds__(256) k_tc5_ids(const WinSpace ws, const uint32_t *__restrict__ uniq, const uint32_t *__restrict__ n_unique_p,
+__global__ void __launch_bounds__(128) k_tc5_ids(const WinSpace ws, const uint32_t *__restrict__ uniq, const uint32_t *__restrict__ n_unique_p,
                                                  uint8_t *__restrict__ ids) {
     const uint32_t n_unique = *n_unique_p;
     const uint32_t npairs = (n_unique + 255) / 256;
+    // Thread t owns ranks 2t and 2t+1 of the pair: in window order these are usually the '+' and the '-' window of ONE column offset
+    // (the unique list is in order of first occurrence), which share their three bytes per species: one set of loads, both codons,
+    // one 16-bit store.  Anything else (a duplicate removed in between, the tracks of a window list) takes the two-window path.
     for (uint32_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-        const uint32_t u = pair * 256 + threadIdx.x;
-        const uint32_t lw = uniq[u < n_unique ? u : n_unique - 1];
-        int64_t o; uint32_t strand;
-        if (ws.mode == 0) { o = ws.c0 + (lw >> 1); strand = lw & 1; }
-        else { o = ws.win_off[lw]; strand = 0; }
-        const uint8_t *p = ws.codes + o;
-        uint8_t *out = ids + (size_t)pair * 2 * ws.nl * 128 + (size_t)(threadIdx.x >> 7) * ws.nl * 128 + (threadIdx.x & 127);
-        for (int s0 = 0; s0 < ws.nl; s0 += 16) {
-            uint32_t v[16][3];
+        const uint32_t u0 = pair * 256 + 2 * threadIdx.x, u1 = u0 + 1;
+        const uint32_t lw0 = uniq[u0 < n_unique ? u0 : n_unique - 1], lw1 = uniq[u1 < n_unique ? u1 : n_unique - 1];
+        uint8_t *out = ids + (size_t)pair * 2 * ws.nl * 128 + (size_t)(threadIdx.x >> 6) * ws.nl * 128 + ((2 * threadIdx.x) & 127);
+        if (ws.mode == 0 && (lw0 & 1) == 0 && lw1 == lw0 + 1) {
+            const uint8_t *p = ws.codes + ws.c0 + (lw0 >> 1);
+            for (int s0 = 0; s0 < ws.nl; s0 += 16) {
+                uint32_t v[16][3];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const uint8_t *q = p + (int64_t)(s0 + k < ws.nl ? s0 + k : s0) * ws.ld;
-                v[k][0] = __ldg(q); v[k][1] = __ldg(q + 1); v[k][2] = __ldg(q + 2);
+                for (int k = 0; k < 16; ++k) {
+                    const uint8_t *q = p + (int64_t)(s0 + k < ws.nl ? s0 + k : s0) * ws.ld;
+                    v[k][0] = __ldg(q); v[k][1] = __ldg(q + 1); v[k][2] = __ldg(q + 2);
+                }
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    if (s0 + k < ws.nl)
+                        *reinterpret_cast<uint16_t *>(out + (size_t)(s0 + k) * 128) =
+                            (uint16_t)(codon_plus(v[k][0], v[k][1], v[k][2]) | (codon_minus(v[k][0], v[k][1], v[k][2]) << 8));
             }
+            continue;
+        }
 #pragma unroll
-            for (int k = 0; k < 16; ++k)
-                if (s0 + k < ws.nl)
-                    out[(size_t)(s0 + k) * 128] = (uint8_t)(strand ? codon_minus(v[k][0], v[k][1], v[k][2]) : codon_plus(v[k][0], v[k][1], v[k][2]));
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t lw = h ? lw1 : lw0;
+            int64_t o; uint32_t strand;
+            if (ws.mode == 0) { o = ws.c0 + (lw >> 1); strand = lw & 1; }
+            else { o = ws.win_off[lw]; strand = 0; }
+            const uint8_t *p = ws.codes + o;
+            for (int s0 = 0; s0 < ws.nl; s0 += 16) {
+                uint32_t v[16][3];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const uint8_t *q = p + (int64_t)(s0 + k < ws.nl ? s0 + k : s0) * ws.ld;
+                    v[k][0] = __ldg(q); v[k][1] = __ldg(q + 1); v[k][2] = __ldg(q + 2);
+                }
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    if (s0 + k < ws.nl)
+                        out[(size_t)(s0 + k) * 128 + h] = (uint8_t)(strand ? codon_minus(v[k][0], v[k][1], v[k][2]) : codon_plus(v[k][0], v[k][1], v[k][2]));
+            }
         }
     }
 }

@@ -110,29 +110,6 @@ struct ModelPool {
     void destroy() { for (const Entry &e : all) pcsf_model_destroy(e.m); all.clear(); free_models.clear(); }
 };
 
-// Page-locked host buffer that only grows (25 % headroom): the matrices and score vectors of a worker thread are handed to
-// pcsf_tracks call after call, so the DMA engines copy them without a staging pass.
-struct PinnedBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    double alloc_seconds = 0.0;
-    PinnedBuf() = default;
-    PinnedBuf(const PinnedBuf &) = delete;
-    ~PinnedBuf() { pcsf_free_pinned(p); }
-    template <class T> T *get(size_t n) {
-        const size_t bytes = n * sizeof(T);
-        if (bytes > cap) {
-            const auto t0 = std::chrono::steady_clock::now();
-            pcsf_free_pinned(p);
-            cap = bytes + bytes / 4 + 4096;
-            p = pcsf_alloc_pinned(cap);
-            alloc_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-            if (!p) die("cannot allocate %zu bytes of page-locked memory: %s", cap, pcsf_last_error());
-        }
-        return reinterpret_cast<T *>(p);
-    }
-};
-
 int default_gpus() { return std::max(1, pcsf_device_count()); }
 
 // One thread per GPU prepares that GPU's models one after the other (host work: eigensystem, all P(t), tables; then the uploads) and

@@ -195,8 +195,11 @@ __device__ __forceinline__ bool same_pattern(const WinSpace &ws, uint32_t w1, ui
     return true;
 }
 
+// table[slot] ends up holding the SMALLEST window id of the pattern that owns the slot: the first window of a pattern claims an empty
+// slot with a CAS, every later one lowers the entry with atomicMin.  Whoever sits in a slot at any moment has the slot's pattern (entries
+// only change from EMPTY to a window, or to a smaller window of the same pattern), so a probe may compare with whatever it reads.
 __global__ void k_insert(WinSpace ws, const uint64_t *__restrict__ klo, const uint64_t *__restrict__ khi, uint32_t nwin,
-                         uint32_t *table, uint32_t tmask, uint32_t *__restrict__ slot_of, uint32_t *slotmin) {
+                         uint32_t *table, uint32_t tmask, uint32_t *__restrict__ slot_of) {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= nwin) return;
     const uint64_t a = klo[w], b = khi[w];
@@ -208,19 +211,22 @@ __global__ void k_insert(WinSpace ws, const uint64_t *__restrict__ klo, const ui
             if (prev == EMPTY) break;
             cur = prev;
         }
-        if (cur == w || (klo[cur] == a && khi[cur] == b && same_pattern(ws, w, cur))) break;
+        if (cur == w) break;
+        if (klo[cur] == a && khi[cur] == b && same_pattern(ws, w, cur)) {
+            if (w < cur) atomicMin(table + slot, w);
+            break;
+        }
         slot = (slot + 1) & tmask;
     }
     slot_of[w] = slot;
-    atomicMin(slotmin + slot, w);
 }
 
-// rep[w] = smallest window id with the same key; flag[w] = (rep[w] == w).  rep overwrites slot_of.
-__global__ void k_resolve(uint32_t nwin, uint32_t *__restrict__ slot_of_rep, const uint32_t *__restrict__ slotmin,
+// rep[w] = smallest window id with the same pattern; flag[w] = (rep[w] == w).  rep overwrites slot_of.
+__global__ void k_resolve(uint32_t nwin, uint32_t *__restrict__ slot_of_rep, const uint32_t *__restrict__ table,
                           uint32_t *__restrict__ flag) {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= nwin) return;
-    const uint32_t rep = slotmin[slot_of_rep[w]];
+    const uint32_t rep = table[slot_of_rep[w]];
     slot_of_rep[w] = rep;
     flag[w] = (rep == w);
 }

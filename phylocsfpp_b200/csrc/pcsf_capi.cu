@@ -93,7 +93,7 @@ struct pcsf_model {
     float *d_bl = nullptr;
     int32_t *d_gemm_edges = nullptr;
     // scratch
-    DevBuf codes, klo, khi, slot, flag, uniq, pidx, table, slotmin, bsums, logz, anc, misc, io_in, io_out, perwin, mle;
+    DevBuf codes, klo, khi, slot, flag, uniq, pidx, table, bsums, logz, anc, misc, io_in, io_out, perwin, mle;
     int *d_bad = nullptr;
     uint32_t *d_nuniq = nullptr;       // [max chunks]
     int64_t chunk_cols = (int64_t)1 << 21;          // 2 Mi columns: calls of 4 Mi columns and more are pipelined (H2D | compute | D2H per chunk)
@@ -241,7 +241,7 @@ extern "C" void pcsf_model_destroy(pcsf_model *m) {
     if (m->h2d_stream) cudaStreamDestroy(m->h2d_stream);
     for (cudaEvent_t e : m->ev_h2d) cudaEventDestroy(e);
     if (m->ev_chunk) cudaEventDestroy(m->ev_chunk);
-    DevBuf *bufs[] = {&m->codes, &m->klo, &m->khi, &m->slot, &m->flag, &m->uniq, &m->pidx, &m->table, &m->slotmin,
+    DevBuf *bufs[] = {&m->codes, &m->klo, &m->khi, &m->slot, &m->flag, &m->uniq, &m->pidx, &m->table,
                       &m->bsums, &m->logz, &m->anc, &m->misc, &m->io_in, &m->io_out, &m->perwin, &m->mle, &m->tc5_ids};
     for (DevBuf *b : bufs) b->release();
     for (auto &e : m->ev) if (e) cudaEventDestroy(e);
@@ -317,15 +317,13 @@ static pcsf_status dedup_and_prune(pcsf_model *m, const WinSpace &ws, uint32_t n
         const uint32_t T = next_pow2((uint64_t)nwin * 2 < 1024 ? 1024 : (uint64_t)nwin * 2);
         const uint32_t nsb = (nwin + SCAN_BLOCK - 1) / SCAN_BLOCK;
         CK(m->table.reserve((size_t)T * 4));
-        CK(m->slotmin.reserve((size_t)T * 4));
         CK(m->slot.reserve((size_t)nwin * 4));
         CK(m->flag.reserve((size_t)nwin * 4));
         CK(m->bsums.reserve((size_t)(nsb + 1) * 4));
         CK(cudaMemsetAsync(m->table.p, 0xFF, (size_t)T * 4, st));
-        CK(cudaMemsetAsync(m->slotmin.p, 0xFF, (size_t)T * 4, st));
         m->launches += 5; k_insert<<<nblk, TB, 0, st>>>(ws, m->klo.as<uint64_t>(), m->khi.as<uint64_t>(), nwin, m->table.as<uint32_t>(), T - 1,
-                                      m->slot.as<uint32_t>(), m->slotmin.as<uint32_t>());
-        k_resolve<<<nblk, TB, 0, st>>>(nwin, m->slot.as<uint32_t>(), m->slotmin.as<uint32_t>(), m->flag.as<uint32_t>());
+                                      m->slot.as<uint32_t>());
+        k_resolve<<<nblk, TB, 0, st>>>(nwin, m->slot.as<uint32_t>(), m->table.as<uint32_t>(), m->flag.as<uint32_t>());
         k_scan_blocks<<<nsb, SCAN_THREADS, 0, st>>>(m->flag.as<uint32_t>(), nwin, m->bsums.as<uint32_t>());
         k_scan_sums<<<1, 1024, 0, st>>>(m->bsums.as<uint32_t>(), nsb, d_nuniq_slot);
         k_finalize<<<nblk, TB, 0, st>>>(nwin, m->slot.as<uint32_t>(), m->flag.as<uint32_t>(), m->bsums.as<uint32_t>(),

@@ -204,6 +204,13 @@ int main_build_tracks(int argc, char **argv) {
     const int per_gpu = getenv("PCSF_HOST_MODELS_PER_GPU") ? std::max(1, atoi(getenv("PCSF_HOST_MODELS_PER_GPU"))) : 2;
     const bool dev_timing = getenv("PCSF_HOST_TIMING") != nullptr;          // per-stage CUDA-event times of every library call (diagnostic)
     std::atomic<double> t_first_model{0.0};
+    // A group is scored in pieces of PIECE_COLS columns through a small page-locked buffer owned by the worker thread: the piece is
+    // copied in BEFORE a model is taken, so a model is held for the library call only (DMA in, kernels, DMA out) and the thread's own
+    // copies overlap the calls of the others.  Pinning the workers' whole staging (16 x 82 MB) costs more than DMA copies save on
+    // anything but very long runs (see below); 21 MB per thread costs 20 ms each, behind the model preparation.
+    const int64_t PIECE_COLS = getenv("PCSF_HOST_PIECE_COLS") ? std::max<int64_t>(1024, atoll(getenv("PCSF_HOST_PIECE_COLS"))) : (1 << 18);
+    const size_t pin_in_bytes = ((size_t)nl * (PIECE_COLS + 2) + 255) / 256 * 256, pin_vec_bytes = ((size_t)(PIECE_COLS + 2) * 8 + 255) / 256 * 256;
+    const size_t pin_bytes = pin_in_bytes + 3 * pin_vec_bytes;
     std::thread pool_maker([&] {
         fill_pool(model, gpus, per_gpu, pool, stop_models, allowed_gpus, [&](pcsf_model *dm) {
             if (dev_timing) pcsf_set_timing(dm, 1);
@@ -265,10 +272,10 @@ int main_build_tracks(int argc, char **argv) {
     // scores ~60-100 M columns/s through this host: one device per 60 M columns (PCSF_HOST_USE_ALL_GPUS=1: all of --gpus).
     const int gpus_worth = getenv("PCSF_HOST_USE_ALL_GPUS") ? gpus : (int)std::min<int64_t>(gpus, std::max<int64_t>(1, (cols_before + 30000000) / 60000000));
     allowed_gpus = gpus_worth;
-    // Staging, one region per worker, sized by the largest group (known exactly from the scan).  Pinning runs at 1-2 GB/s and competes
-    // with the model preparation for the driver, so the regions are plain page-aligned memory that the workers parse into from the
-    // first millisecond; once the models are up a background thread page-locks them in place, one after the other
-    // (pcsf_register_host).  Calls made before a region is pinned are simply staged by the driver.
+    // Staging, one region per worker, sized by the largest group (known exactly from the scan): plain page-aligned memory that the
+    // workers parse into and format from.  (Page-locking it was measured in three ways — per thread, as one slab, in place in the
+    // background — and always cost more than it saved below ~400 M columns: 1-2 GB/s, serialised in the driver, and the library
+    // calls of the other threads crawl meanwhile.  The DMA path comes from the small per-model staging instead.)
     int64_t max_group_cols = 1;
     for (const Group &g : groups) {
         int64_t n = 0;
@@ -282,20 +289,11 @@ int main_build_tracks(int argc, char **argv) {
     std::vector<uint8_t *> slabs(slab_threads, nullptr);
     for (auto &p : slabs)
         if (posix_memalign(reinterpret_cast<void **>(&p), 4096, per_thread) != 0) die("cannot allocate %zu bytes of staging memory", per_thread);
-    std::atomic<bool> stop_pinning{false};
-    std::vector<char> pinned(slab_threads, 0);
-    double t_slab = 0.0, t_startup = 0.0;
+    double t_startup = 0.0;
+    const double t_slab = 0.0;
     std::thread pool_waiter([&] {
         pool_maker.join();
         t_startup = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
-        // Pinning pays only on long runs: ~1 s per GB during which the library calls of the other threads crawl (measured: 100 M
-        // columns take 1.9 s unpinned, 2.5-3.0 s with any pinning scheme), against 0.4 s saved per 100 M columns once pinned.
-        const char *pin_env = getenv("PCSF_HOST_PINNING");
-        const bool pin = pin_env ? atoi(pin_env) != 0 : cols_before >= (int64_t)400000000;
-        if (!pin) return;
-        const auto a0 = std::chrono::steady_clock::now();
-        for (int t = 0; t < slab_threads && !stop_pinning; ++t) pinned[t] = pcsf_register_host(slabs[t], per_thread) == PCSF_OK;
-        t_slab = std::chrono::duration<double>(std::chrono::steady_clock::now() - a0).count();
     });
     OrderedSink sink;
     sink.resize(total_chains);
@@ -316,6 +314,7 @@ int main_build_tracks(int argc, char **argv) {
                 if (t >= slab_threads) return;          // fewer groups than threads
                 std::vector<Alignment> alns;
                 uint8_t *const my_slab = slabs[t];
+                uint8_t *my_pin = nullptr;          // page-locked piece buffer, allocated at the first call (after the thread's first parse)
                 std::vector<uint8_t> fallback_mat;          // only for a group whose text disagrees with its size fields
                 std::vector<double> fallback_out;
                 const uint8_t *src = nullptr;
@@ -379,24 +378,48 @@ int main_build_tracks(int argc, char **argv) {
                         }
                         const auto p1 = now();
                         my_parse += secs(p0, p1);
-                        const ModelPool::Entry me = pool.acquire();
-                        pcsf_model *dm = me.m;
-                        const auto g0 = now();
-                        my_wait_model += secs(p1, g0);
-                        pcsf_tracks_stats cs{};
-                        const pcsf_status st = pcsf_tracks(dm, src, Ltot, Ltot, PCSF_TRACKS_BLS | (raw ? PCSF_TRACKS_SCORES : 0) | pflag,
-                                                           plus, minus, bls, nullptr, &cs);
-                        my_gpu += secs(g0, now());
-                        if (dev_timing) {
-                            std::lock_guard<std::mutex> g(gpu_time_mu);
-                            dev_ms[0] += cs.ms_pack; dev_ms[1] += cs.ms_hash; dev_ms[2] += cs.ms_dedup; dev_ms[3] += cs.ms_prune; dev_ms[4] += cs.ms_scatter;
-                            dev_ms[5] += cs.ms_bls; dev_unique += cs.n_unique; dev_windows += cs.n_windows;
+                        // piece by piece through a model's page-locked staging: windows [w0, w1) need columns [w0, w1 + 2); the last
+                        // piece also takes the trailing columns (BLS is per column).  Every window is scored exactly once, so the result
+                        // is that of one call over the whole group.
+                        const int64_t Wtot = std::max<int64_t>(Ltot - 2, 0);
+                        const uint32_t call_flags = PCSF_TRACKS_BLS | (raw ? PCSF_TRACKS_SCORES : 0) | pflag;
+                        for (int64_t w0 = 0; w0 == 0 || w0 < Wtot; w0 += PIECE_COLS) {
+                            const int64_t w1 = std::min(Wtot, w0 + PIECE_COLS);
+                            const bool last_piece = w1 >= Wtot;
+                            const int64_t cend = last_piece ? Ltot : w1 + 2, w = cend - w0;
+                            if (!my_pin) {
+                                my_pin = static_cast<uint8_t *>(pcsf_alloc_pinned(pin_bytes));
+                                if (!my_pin) die("cannot allocate %zu bytes of page-locked memory: %s", pin_bytes, pcsf_last_error());
+                            }
+                            uint8_t *pin_in = my_pin;
+                            double *pin_plus = reinterpret_cast<double *>(my_pin + pin_in_bytes), *pin_minus = reinterpret_cast<double *>(my_pin + pin_in_bytes + pin_vec_bytes),
+                                   *pin_bls = reinterpret_cast<double *>(my_pin + pin_in_bytes + 2 * pin_vec_bytes);
+                            for (int s2 = 0; s2 < nl; ++s2) memcpy(pin_in + (size_t)s2 * w, src + (size_t)s2 * Ltot + w0, (size_t)w);
+                            const auto q0 = now();
+                            const ModelPool::Entry me = pool.acquire();
+                            const auto g0 = now();
+                            my_wait_model += secs(q0, g0);
+                            pcsf_tracks_stats cs{};
+                            const pcsf_status st = pcsf_tracks(me.m, pin_in, w, w, call_flags, pin_plus, pin_minus, pin_bls, nullptr, &cs);
+                            my_gpu += secs(g0, now());
+                            pool.release(me);
+                            if (st == PCSF_OK) {
+                                if (raw && w1 > w0) {
+                                    memcpy(plus + w0, pin_plus, (size_t)(w1 - w0) * 8);
+                                    memcpy(minus + w0, pin_minus, (size_t)(w1 - w0) * 8);
+                                }
+                                memcpy(bls + w0, pin_bls, (size_t)(last_piece ? w : w1 - w0) * 8);
+                            }
+                            if (dev_timing) {
+                                std::lock_guard<std::mutex> g(gpu_time_mu);
+                                dev_ms[0] += cs.ms_pack; dev_ms[1] += cs.ms_hash; dev_ms[2] += cs.ms_dedup; dev_ms[3] += cs.ms_prune; dev_ms[4] += cs.ms_scatter;
+                                dev_ms[5] += cs.ms_bls; dev_unique += cs.n_unique; dev_windows += cs.n_windows;
+                            }
+                            if (st == PCSF_ERR_BAD_CHAR) { fprintf(stderr, "%s\n", pcsf_last_error()); exit(37); }      // translation.hpp:46-51
+                            if (st != PCSF_OK) die("pcsf_tracks: %s", pcsf_last_error());
+                            gpu_cols[me.dev] += w1 > w0 ? w1 - w0 : w;
                         }
-                        pool.release(me);
-                        if (st == PCSF_ERR_BAD_CHAR) { fprintf(stderr, "%s\n", pcsf_last_error()); exit(37); }      // translation.hpp:46-51
-                        if (st != PCSF_OK) die("pcsf_tracks: %s", pcsf_last_error());
                         cols += Ltot;
-                        gpu_cols[me.dev] += Ltot;
                     }
                     const auto f0 = now();
                     for (size_t ci = c0; ci < c1; ++ci) {
@@ -504,7 +527,6 @@ int main_build_tracks(int argc, char **argv) {
         }
     }
     for (auto &w : workers) w.join();
-    stop_pinning = true;
     stop_models = true;
     pool_waiter.join();
     total_cols += cols;
@@ -554,7 +576,7 @@ int main_build_tracks(int argc, char **argv) {
         _exit(0);
     }
     const auto x0 = std::chrono::steady_clock::now();
-    for (int t = 0; t < slab_threads; ++t) { if (pinned[t]) pcsf_unregister_host(slabs[t]); free(slabs[t]); }
+    for (int t = 0; t < slab_threads; ++t) free(slabs[t]);
     const auto x1 = std::chrono::steady_clock::now();
     pool.destroy();
     const auto x2 = std::chrono::steady_clock::now();

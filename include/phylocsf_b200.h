@@ -75,9 +75,8 @@ void pcsf_model_destroy(pcsf_model *m);
  * are reused across many calls (measured: the command line host on a 10 M-column file is faster with pageable vectors). */
 void *pcsf_alloc_pinned(size_t bytes);
 void pcsf_free_pinned(void *p);
-/* Page-locks memory the caller already owns (and may already be using): the command line host parses into plain page-aligned buffers
- * from the first millisecond and a background thread pins them one by one — calls made before a buffer is pinned work, their copies
- * are just staged by the driver.  p and bytes should be multiples of the page size. */
+/* Page-locks memory the caller already owns (and may already be using), e.g. long-lived staging buffers of a driver: calls made before
+ * a buffer is pinned work, their copies are just staged by the driver.  p and bytes should be multiples of the page size. */
 pcsf_status pcsf_register_host(void *p, size_t bytes);
 pcsf_status pcsf_unregister_host(void *p);
 

@@ -266,7 +266,7 @@ def test_tcgen05_path_properties_at_scale():
     """BASELINE-scale properties of the tcgen05 path (2 Mi columns of the config-3 shape, 58mammals): every window is
     computed independently and deterministically, so (a) two runs are bit-identical, (b) the '-' track of S equals the
     '+' track of revcomp(S) read backwards, bit for bit, although the windows land in other tiles, lanes and chains,
-    (c) 4096 random windows agree with the FP64 path within the 1e-3 deciban contract (asserted at 3e-4)."""
+    (c) all 4.2 M windows agree with the FP64 path within the 1e-3 deciban contract (asserted at 3e-4)."""
     import torch
     from phylocsfpp_b200.synth import synth_alignment
     model = load_model("58mammals")
@@ -278,11 +278,12 @@ def test_tcgen05_path_properties_at_scale():
     assert np.array_equal(a["plus"], a2["plus"]) and np.array_equal(a["minus"], a2["minus"])
     b = dm.tracks(orc.reverse_complement(seqs), bls=False, tc5=True)
     assert np.array_equal(a["minus"], b["plus"][::-1]) and np.array_equal(a["plus"], b["minus"][::-1])
-    idx = np.sort(np.random.default_rng(1).integers(0, L - 2, 4096))
-    sub = np.concatenate([seqs[:, i:i + 3] for i in idx], axis=1)          # 3-column snippets: window 3k is snippet k
-    f64 = dm.tracks(sub, bls=False)
-    assert np.abs(f64["plus"][0::3][:idx.size] - a["plus"][idx]).max() <= 3e-4
-    assert np.abs(f64["minus"][0::3][:idx.size] - a["minus"][idx]).max() <= 3e-4
+    # (c) EVERY one of the 4.2 M windows against the FP64 DMMA path (the parity anchor, itself within 1e-6 of the oracle): contract
+    # 1e-3 decibans, asserted at 3e-4
+    f64 = dm.tracks(seqs, bls=False)
+    dp, dmn = np.abs(f64["plus"] - a["plus"]).max(), np.abs(f64["minus"] - a["minus"]).max()
+    print(f"58mammals, {2 * (L - 2)} windows: tcgen05 path max |delta| vs FP64 path = {max(dp, dmn):.3e} decibans")
+    assert dp <= 3e-4 and dmn <= 3e-4
     assert np.isfinite(a["plus"]).all() and np.isfinite(a["minus"]).all()
     dm.close()
 

@@ -262,15 +262,15 @@ def test_tcgen05_path_extreme_columns_do_not_underflow():
     dm.close()
 
 
-def test_tcgen05_path_properties_at_scale():
-    """BASELINE-scale properties of the tcgen05 path (2 Mi columns of the config-3 shape, 58mammals): every window is
+@pytest.mark.parametrize("name,L", [("58mammals", 1 << 21), ("100vertebrates", 1 << 20)])
+def test_tcgen05_path_properties_at_scale(name, L):
+    """BASELINE-scale properties of the tcgen05 path (2 Mi columns of the config-3 shape, 58mammals; 1 Mi of config 4's 100vertebrates): every window is
     computed independently and deterministically, so (a) two runs are bit-identical, (b) the '-' track of S equals the
     '+' track of revcomp(S) read backwards, bit for bit, although the windows land in other tiles, lanes and chains,
     (c) all 4.2 M windows agree with the FP64 path within the 1e-3 deciban contract (asserted at 3e-4)."""
     import torch
     from phylocsfpp_b200.synth import synth_alignment
-    model = load_model("58mammals")
-    L = 1 << 21
+    model = load_model(name)
     seqs = synth_alignment(model, L, seed=99, device="cpu")[:, :L].numpy()
     dm = capi.DeviceModel(model)
     a = dm.tracks(seqs, bls=False, tc5=True)
@@ -282,7 +282,7 @@ def test_tcgen05_path_properties_at_scale():
     # 1e-3 decibans, asserted at 3e-4
     f64 = dm.tracks(seqs, bls=False)
     dp, dmn = np.abs(f64["plus"] - a["plus"]).max(), np.abs(f64["minus"] - a["minus"]).max()
-    print(f"58mammals, {2 * (L - 2)} windows: tcgen05 path max |delta| vs FP64 path = {max(dp, dmn):.3e} decibans")
+    print(f"{name}, {2 * (L - 2)} windows: tcgen05 path max |delta| vs FP64 path = {max(dp, dmn):.3e} decibans")
     assert dp <= 3e-4 and dmn <= 3e-4
     assert np.isfinite(a["plus"]).all() and np.isfinite(a["minus"]).all()
     dm.close()

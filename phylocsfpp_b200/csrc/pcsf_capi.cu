@@ -86,6 +86,8 @@ struct pcsf_model {
     size_t prune_tc5_smem = 0;
     int tc5_nstage = 2, tc5_nids = 1;
     MleStats msa_stats;                  // of the last MLE score-msa call
+    uint8_t *h_msa = nullptr;            // page-locked staging of pcsf_score_msa's concatenated [nl][Ltot] matrix (grows with 25 % headroom)
+    size_t h_msa_cap = 0;
     DevBuf tc5_ids;                      // codon ids of the unique windows, [pairs][2][nl][128] (k_tc5_ids)
     int32_t *d_program = nullptr;
     BlsInner *d_bls_prog = nullptr;
@@ -236,6 +238,7 @@ extern "C" void pcsf_model_destroy(pcsf_model *m) {
     }
     cudaFree(m->d_program); cudaFree(m->d_bls_prog); cudaFree(m->d_bls_tables); cudaFree(m->d_bl); cudaFree(m->d_gemm_edges);
     cudaFree(m->d_bad); cudaFree(m->d_nuniq); cudaFree(m->d_tc5_steps); cudaFree(m->d_tc5_scratch); cudaFree(m->d_tc5_srcs);
+    if (m->h_msa) cudaFreeHost(m->h_msa);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     if (m->h2d_stream) cudaStreamDestroy(m->h2d_stream);
@@ -685,15 +688,30 @@ extern "C" pcsf_status pcsf_score_msa(pcsf_model *m, pcsf_strategy strategy, int
     if (Ltot >= ((int64_t)1 << 32) || nwin >= ((int64_t)1 << 31))
         return fail(PCSF_ERR_INVALID, "batch too large: split the call");
     const int64_t ldd = ((Ltot + 15) / 16) * 16;
-    std::vector<uint8_t> h((size_t)ldd * nl, (uint8_t)'N');
-    for (int i = 0; i < n_aln; ++i)
-        for (int s = 0; s < nl; ++s)
-            memcpy(h.data() + (size_t)s * ldd + col_start[i], seqs + offset[i] + (size_t)s * len[i], (size_t)len[i]);
+    // the batch side by side in the handle's page-locked staging (allocated once, re-used by every call: plain DMA, no fresh 100 MB
+    // vector per call); only the two pad columns behind every alignment and the tail are filled with N
+    const size_t h_bytes = (size_t)ldd * nl;
+    if (h_bytes > m->h_msa_cap) {
+        if (m->h_msa) cudaFreeHost(m->h_msa);
+        m->h_msa = nullptr;
+        m->h_msa_cap = h_bytes + h_bytes / 4 + 4096;
+        CK(cudaHostAlloc(reinterpret_cast<void **>(&m->h_msa), m->h_msa_cap, cudaHostAllocPortable));
+    }
+    uint8_t *h = m->h_msa;
+    for (int s = 0; s < nl; ++s) {
+        uint8_t *row = h + (size_t)s * ldd;
+        for (int i = 0; i < n_aln; ++i) {
+            memcpy(row + col_start[i], seqs + offset[i] + (size_t)s * len[i], (size_t)len[i]);
+            row[col_start[i] + len[i]] = 'N';
+            row[col_start[i] + len[i] + 1] = 'N';
+        }
+        memset(row + Ltot, 'N', (size_t)(ldd - Ltot));
+    }
     std::vector<uint32_t> win_off((size_t)std::max<int64_t>(nwin, 1));
     for (int i = 0; i < n_aln; ++i)
         for (int64_t k = 0; k < len[i] / 3; ++k) win_off[win_start[i] + k] = (uint32_t)(col_start[i] + 3 * k);
-    CK(m->io_in.reserve(h.size()));
-    CK(cudaMemcpyAsync(m->io_in.p, h.data(), h.size(), cudaMemcpyHostToDevice, st));
+    CK(m->io_in.reserve(h_bytes));
+    CK(cudaMemcpyAsync(m->io_in.p, h, h_bytes, cudaMemcpyHostToDevice, st));
     pcsf_status rc;
     if ((rc = run_pack(m, m->io_in.as<uint8_t>(), Ltot, ldd, st))) return rc;
     // misc: win_off | col_start | win_start | len | outputs

@@ -418,7 +418,8 @@ static pcsf_status run_pack(pcsf_model *m, const uint8_t *d_seqs, int64_t L, int
     CK(m->codes.reserve((size_t)m->codes_ld * nl));
     CK(cudaMemsetAsync(m->d_bad, 0, sizeof(int), st));
     const int64_t nvec = m->codes_ld / 16;
-    dim3 grid((unsigned)std::min<int64_t>((nvec + 255) / 256, 65535), nl);
+    // a few fat blocks per SM with grid-stride loops (four vectors in flight per thread) instead of one block per 4 KB of a row
+    dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>((nvec + 255) / 256, ((int64_t)m->sm_count * 16 + nl - 1) / nl)), nl);
     NvtxRange nvtx_("pcsf: pack");
     m->launches++; k_pack<<<grid, 256, 0, st>>>(d_seqs, L, ld, nl, m->codes.as<uint8_t>(), m->codes_ld, m->codes_ld, m->d_bad);
     CK(cudaGetLastError());
